@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- VB E-step throughput (points/s) of one VB iteration at fixed K.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps K --warmup W      # the reference's CPU path
+
+A "step" is one loop body of vbem() (src/cluster.cpp:203-226) over the whole
+synthetic matrix at fixed K: sufficient statistics of the current
+responsibilities -> posterior update -> E-step (new responsibilities) -> F.
+Workload (BASELINE.json metric): N = 50M rows, D = 128, K = 64 full-covariance
+(GaussWish) clusters, Dirichlet weights (learnBGMM's pair); rows are sharded
+over the ranks (strong scaling: N is the total), one all-reduce of the packed
+statistics per iteration.  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK = 250_000          # rows per generation chunk; shards are whole chunks
+SEED = 20260925
+# fallback only if MEASURED_PEAKS.json is absent (/opt/skills/guides/B200_PROFILING.md)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-points", type=int, default=50_000_000)
+    ap.add_argument("--dim", type=int, default=128)
+    ap.add_argument("--clusters", type=int, default=64)
+    ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            d["_source"] = "measured"
+            return d
+        except Exception:
+            pass
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+# ------------------------------------------------------------------ data ---
+def mixture_params(D, K):
+    """means U(-10,10)^D, covariances A A^T / D + 0.5 I, weights Dirichlet(5)."""
+    rng = np.random.default_rng(SEED)
+    mu = rng.uniform(-10, 10, size=(K, D))
+    L = np.empty((K, D, D))
+    for k in range(K):
+        A = rng.normal(size=(D, D))
+        L[k] = np.linalg.cholesky(A @ A.T / D + 0.5 * np.eye(D))
+    w = rng.dirichlet(5.0 * np.ones(K))
+    return mu, L, w
+
+
+def gen_chunk_torch(torch, dev, c, rows, D, K, mu_t, L_t, w_t):
+    g = torch.Generator(device=dev).manual_seed(SEED + 1 + c)
+    z = torch.multinomial(w_t, rows, replacement=True, generator=g).to(torch.int32)
+    e = torch.randn(rows, D, device=dev, generator=g)
+    x = torch.empty(rows, D, device=dev, dtype=torch.float32)
+    zl = z.long()
+    order = torch.argsort(zl)
+    counts = torch.bincount(zl, minlength=K).tolist()
+    o = 0
+    for k in range(K):
+        n = counts[k]
+        if n:
+            idx = order[o:o + n]
+            x[idx] = mu_t[k] + e[idx] @ L_t[k].T
+            o += n
+    return x, z
+
+
+def gen_rows_numpy(first_rows, D, K):
+    """The same generator family on the host for the CPU sample (independent stream)."""
+    mu, L, w = mixture_params(D, K)
+    rng = np.random.default_rng(SEED + 7)
+    z = rng.choice(K, size=first_rows, p=w)
+    X = mu[z] + np.einsum("nd,ned->ne", rng.normal(size=(first_rows, D)), L[z])
+    return X, z
+
+
+# ------------------------------------------------------- clocks sampling ---
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------- CPU baseline ---
+def cpu_iteration_rate(D, K, budget_s, reps=1):
+    """Oracle (restated reference, fp64, 1 core: the J=1 entry points are effectively
+    single-threaded) on a bounded sample of the same mixture."""
+    from oracle import pyoracle as po
+    Xs, zs = gen_rows_numpy(1024, D, K)
+    q0 = np.zeros((1024, K)); q0[np.arange(1024), zs] = 1.0
+    m = po.Model(po.BGMM, [Xs])
+    t0 = time.perf_counter()
+    m.vbem(q0, maxit=0)
+    per_row = (time.perf_counter() - t0) / 1024
+    rows = int(min(1 << 17, max(2048, budget_s / max(per_row, 1e-9) / max(reps, 1))))
+    X, z = gen_rows_numpy(rows, D, K)
+    q0 = np.zeros((rows, K)); q0[np.arange(rows), z] = 1.0
+    m = po.Model(po.BGMM, [X])
+    m.vbem(q0, maxit=0)                      # responsibilities now soft; clusters initialised
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        m.iteration()
+        times.append(time.perf_counter() - t0)
+    return rows, times
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    D, K = a.dim, a.clusters
+    total = a.steps + a.warmup
+    rows, times = cpu_iteration_rate(D, K, budget_s=150.0, reps=total)
+    t = times[a.warmup:] if len(times) > a.warmup else times
+    sec = float(np.mean(t))
+    val = rows / sec
+    line = {
+        "impl": "reference", "metric": "VB E-step points/sec at N=50M D=128 K=64", "value": val, "unit": "points/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "VB iteration (SS + M + E + F), BGMM full-cov, N=%d D=%d K=%d" % (a.n_points, D, K),
+                   "sample_rows": rows, "note": "reference CPU path restated (oracle/vb_oracle.c); Eigen/Boost absent so "
+                   "the reference itself cannot be built; J=1 entry points run on one core (SURVEY.md section 2)"},
+        "cpu_baseline": {"value": val, "unit": "points/s", "cores": 1, "kind": "port",
+                         "sample": "%d rows of the same synthetic mixture, one vbem iteration each step" % rows},
+        "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------- main ---
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+
+    import libcluster_b200 as lc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    N, D, K = a.n_points, a.dim, a.clusters
+    prec = lc.F32 if a.precision == "f32" else lc.F64
+    nchunks = (N + CHUNK - 1) // CHUNK
+    c0, c1 = lc.shard_rows(nchunks, rank, world)
+    r0, r1 = c0 * CHUNK, min(N, c1 * CHUNK)
+    nloc = r1 - r0
+
+    eng = lc.Engine(local, prec)
+    if world > 1:
+        idt = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(lc.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init_nccl(bytes(idt.cpu().numpy().tobytes()), rank, world)
+
+    mu, L, w = mixture_params(D, K)
+    mu_t = torch.tensor(mu, dtype=torch.float32, device=dev)
+    L_t = torch.tensor(L, dtype=torch.float32, device=dev)
+    w_t = torch.tensor(w, dtype=torch.float32, device=dev)
+    X = torch.empty(nloc, D, dtype=torch.float32, device=dev)
+    z = torch.empty(nloc, dtype=torch.int32, device=dev)
+    for c in range(c0, c1):
+        rows = min(CHUNK, N - c * CHUNK)
+        xc, zc = gen_chunk_torch(torch, dev, c, rows, D, K, mu_t, L_t, w_t)
+        o = c * CHUNK - r0
+        X[o:o + rows] = xc
+        z[o:o + rows] = zc
+    torch.cuda.synchronize()
+
+    eng.set_data_device(X.data_ptr(), nloc, D, D)
+    eng.model_init(lc.BGMM)
+    eng.set_labels_device(z.data_ptr(), K)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        eng.vbem_step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, s_ms, e_ms, launches, Fs = 0.0, 0.0, 0.0, 0, []
+    for _ in range(a.steps):
+        Fs.append(eng.vbem_step())
+        t = eng.step_timing()
+        dev_ms += t["step_ms"]; s_ms += t["sstat_ms"]; e_ms += t["estep_ms"]; launches += t["launches"]
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    tt = torch.tensor([dev_ms, wall * 1e3, s_ms, e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms, s_ms, e_ms = [float(v) for v in tt.tolist()]
+    ms_per_step = dev_ms / a.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (device-event time, this run) -------
+    pk = peaks()
+    flops_half = float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
+    if e_ms >= s_ms:
+        kname, kms = "estep_full_kernel", e_ms / a.steps
+    else:
+        kname, kms = "sstat_full_kernel", s_ms / a.steps
+    peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
+    ach_tf = flops_half / (kms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_tf, "traffic": None, "peak_source": pk["_source"] + " bf16_tflops_sustained",
+                "kernel_ms": kms, "hbm_frac": (4.0 * D * nloc / (kms * 1e-3) / 1e9) / pk["hbm_gbs"],
+                "sstat_ms": s_ms / a.steps, "estep_ms": e_ms / a.steps,
+                "note": "algorithmic K*D^2 flops/point for this half of the pass (fp32 SIMT tier)"}
+
+    # ---- e2e: the same step through the C ABI from HOST buffers ---------------
+    e2e = None
+    if not a.no_e2e:
+        try:
+            e2e = run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a)
+        except Exception as ex:  # noqa: BLE001
+            e2e = {"value": None, "unit": "points/s", "error": str(ex)[:200]}
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        rows, times = cpu_iteration_rate(D, K, budget_s=15.0, reps=1)
+        cpu = {"value": rows / times[0], "unit": "points/s", "cores": 1, "kind": "port",
+               "sample": "%d rows of the same synthetic mixture, one vbem iteration (oracle/vb_oracle.c, fp64)" % rows}
+
+    if rank == 0:
+        line = {
+            "metric": "VB E-step points/sec at N=50M D=128 K=64", "value": value, "unit": "points/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if prec == lc.F32 else "f64", "data": "synthetic",
+            "config": {"workload": "VB iteration (SS + M + E + F), learnBGMM pair (Dirichlet, GaussWish full-cov), "
+                       "N=%d D=%d K=%d" % (N, D, K), "rows_per_gpu": nloc, "parallelism": "rows sharded x%d" % world,
+                       "l2": "inputs (%.1f GB/GPU) far larger than L2" % (nloc * D * 4 / 1e9),
+                       "timing": "CUDA events on the engine stream around each step, summed, max over ranks",
+                       "wall_ms_per_step": wall_ms / a.steps, "F_last": Fs[-1]},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
+    """Every step: host fp64 X (page-locked) -> lcb_set_data -> labels H2D -> one VB iteration -> F on the host."""
+    import psutil
+    need = nloc * D * 8
+    if psutil.virtual_memory().available < 1.5 * need + (8 << 30):
+        raise RuntimeError("not enough host memory for a %d-byte page-locked copy of X" % need)
+    Xh = torch.empty(nloc, D, dtype=torch.float64, pin_memory=True)
+    step = 1 << 20
+    for r in range(0, nloc, step):
+        Xh[r:r + step].copy_(X[r:r + step].double())
+    zh = torch.empty(nloc, dtype=torch.int32, pin_memory=True)
+    zh.copy_(z)
+    torch.cuda.synchronize()
+    Xn = Xh.numpy()
+    zd = torch.empty(nloc, dtype=torch.int32, device=dev)
+    times = []
+    for i in range(1 + a.e2e_steps):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        eng.set_data(Xn)
+        eng.model_init(lc.BGMM)
+        zd.copy_(zh, non_blocking=True)
+        torch.cuda.synchronize()
+        eng.set_labels_device(zd.data_ptr(), K)
+        F = eng.vbem_step()
+        t1 = time.perf_counter()
+        if i > 0:
+            times.append(t1 - t0)
+    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    return {"value": N / sec, "unit": "points/s", "h2d_bytes_per_step": int(need + nloc * 4),
+            "d2h_bytes_per_step": 8, "ms_per_step": sec * 1e3, "steps": a.e2e_steps,
+            "path": "Engine.set_data(host fp64) + set_labels + lcb_vbem_step through the C ABI", "F": F}
+
+
+if __name__ == "__main__":
+    main()

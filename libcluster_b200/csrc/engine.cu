@@ -1,0 +1,1229 @@
+// engine.cu -- see engine.hpp.
+#include "engine.hpp"
+
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <iostream>
+
+#include "kernels.cuh"
+
+namespace lcb {
+
+namespace {
+enum { kF32 = 0, kF64 = 1 };
+
+inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// ---- NCCL by dlopen ------------------------------------------------------
+struct NcclId { char internal[128]; };
+typedef int (*fn_get_id)(NcclId*);
+typedef int (*fn_init_rank)(void**, int, NcclId, int);
+typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_destroy)(void*);
+typedef const char* (*fn_errstr)(int);
+struct NcclApi {
+  void* h = nullptr;
+  fn_get_id get_id = nullptr;
+  fn_init_rank init_rank = nullptr;
+  fn_allreduce allreduce = nullptr;
+  fn_destroy destroy = nullptr;
+  fn_errstr errstr = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.h == nullptr) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (api.h) {
+      api.get_id = (fn_get_id)dlsym(api.h, "ncclGetUniqueId");
+      api.init_rank = (fn_init_rank)dlsym(api.h, "ncclCommInitRank");
+      api.allreduce = (fn_allreduce)dlsym(api.h, "ncclAllReduce");
+      api.destroy = (fn_destroy)dlsym(api.h, "ncclCommDestroy");
+      api.errstr = (fn_errstr)dlsym(api.h, "ncclGetErrorString");
+      api.ok = api.get_id && api.init_rank && api.allreduce && api.destroy;
+    }
+  }
+  return api;
+}
+const int kNcclDouble = 8, kNcclSum = 0;
+}  // namespace
+
+int nccl_get_unique_id(char out[128], std::string* err) {
+  NcclApi& a = nccl();
+  if (!a.ok) {
+    *err = "libnccl.so.2 could not be loaded";
+    return 4;
+  }
+  NcclId id;
+  const int rc = a.get_id(&id);
+  if (rc != 0) {
+    *err = std::string("ncclGetUniqueId: ") + (a.errstr ? a.errstr(rc) : "error");
+    return 4;
+  }
+  std::memcpy(out, id.internal, 128);
+  return 0;
+}
+
+// ---------------------------------------------------------------- plumbing --
+void Engine::check(cudaError_t e, const char* what) const {
+  if (e != cudaSuccess) throw Error{4, std::string(what) + ": " + cudaGetErrorString(e)};
+}
+void Engine::sync() { check(cudaStreamSynchronize(stream_), "stream synchronize"); }
+
+Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
+  if (precision != kF32 && precision != kF64) throw_invalid("precision must be LCB_F32 or LCB_F64");
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0)
+    throw Error{4, "no CUDA device is visible: the VB engine has no CPU fallback"};
+  if (device < 0 || device >= n) throw_invalid("device index out of range");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  cudaDeviceProp prop;
+  check(cudaGetDeviceProperties(&prop, device_), "cudaGetDeviceProperties");
+  sms_ = prop.multiProcessorCount;
+  check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
+  for (auto& e : ev_) check(cudaEventCreate(&e), "cudaEventCreate");
+}
+
+Engine::~Engine() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  free_view(main_);
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_};
+  for (DeviceBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (h_pin_) cudaFreeHost(h_pin_);
+  for (auto& e : ev_)
+    if (e) cudaEventDestroy(e);
+  if (nccl_comm_ && nccl().ok) nccl().destroy(nccl_comm_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Engine::reserve(DeviceBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return;
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  sync();
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = bytes + bytes / 4 + 256;
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) throw Error{5, std::string("cudaMalloc: ") + cudaGetErrorString(e)};
+  b.bytes = want;
+}
+
+void* Engine::pinned(size_t bytes) {
+  if (bytes > h_pin_bytes_) {
+    sync();
+    if (h_pin_) cudaFreeHost(h_pin_);
+    h_pin_ = nullptr;
+    h_pin_bytes_ = 0;
+    size_t want = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaMallocHost(&h_pin_, want);
+    if (e != cudaSuccess) throw Error{5, std::string("cudaMallocHost: ") + cudaGetErrorString(e)};
+    h_pin_bytes_ = want;
+  }
+  return h_pin_;
+}
+
+void Engine::free_view(View& v) {
+  if (v.owns_x && v.X) cudaFree(v.X);
+  if (v.owns_x && v.gid) cudaFree(v.gid);
+  if (v.q) cudaFree(v.q);
+  if (v.q2) cudaFree(v.q2);
+  v = View();
+}
+
+static void dev_alloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes > 0 ? bytes : 16);
+  if (e != cudaSuccess) throw Error{5, std::string("cudaMalloc: ") + cudaGetErrorString(e)};
+}
+
+// Make room for K responsibility columns in both buffers, keeping q's content.
+void Engine::ensure_q(View& v, int K) {
+  if (K <= v.ldq && v.q && v.q2) return;
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  int64_t nld = round_up(std::max<int64_t>(K, 1), 8);
+  if (v.ldq > 0) nld = std::max(nld, std::min<int64_t>(2 * v.ldq, 512));
+  void *nq = nullptr, *nq2 = nullptr;
+  const size_t bytes = (size_t)std::max<int64_t>(v.N, 1) * nld * es;
+  dev_alloc(&nq, bytes);
+  dev_alloc(&nq2, bytes);
+  if (v.q && v.K > 0 && v.N > 0) {
+    if (prec_ == kF32)
+      check(dev::copy_q<float>(stream_, (const float*)v.q, (float*)nq, v.ldq, nld, v.N, v.K, v.K), "copy_q");
+    else
+      check(dev::copy_q<double>(stream_, (const double*)v.q, (double*)nq, v.ldq, nld, v.N, v.K, v.K), "copy_q");
+    sync();
+  }
+  if (v.q) cudaFree(v.q);
+  if (v.q2) cudaFree(v.q2);
+  v.q = nq;
+  v.q2 = nq2;
+  v.ldq = nld;
+}
+
+// ------------------------------------------------------------ communication --
+void Engine::comm_init_nccl(const char id[128], int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world) throw_invalid("bad rank/world");
+  NcclApi& a = nccl();
+  if (!a.ok) throw Error{4, "libnccl.so.2 could not be loaded"};
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  NcclId nid;
+  std::memcpy(nid.internal, id, 128);
+  void* comm = nullptr;
+  const int rc = a.init_rank(&comm, world, nid, rank);
+  if (rc != 0) throw Error{4, std::string("ncclCommInitRank: ") + (a.errstr ? a.errstr(rc) : "error")};
+  nccl_comm_ = comm;
+  host_ar_ = nullptr;
+  rank_ = rank;
+  world_ = world;
+}
+
+void Engine::comm_init_host(HostAllreduceFn fn, void* ctx, int rank, int world) {
+  if (world < 1 || rank < 0 || rank >= world || fn == nullptr) throw_invalid("bad rank/world/callback");
+  host_ar_ = fn;
+  host_ar_ctx_ = ctx;
+  rank_ = rank;
+  world_ = world;
+}
+
+void Engine::allreduce(double* dev, int64_t count) {
+  if (world_ == 1 || count <= 0) return;
+  if (nccl_comm_) {
+    const int rc = nccl().allreduce(dev, dev, (size_t)count, kNcclDouble, kNcclSum, nccl_comm_, stream_);
+    if (rc != 0) throw Error{4, "ncclAllReduce failed"};
+    return;
+  }
+  double* h = (double*)pinned(sizeof(double) * count);
+  check(cudaMemcpyAsync(h, dev, sizeof(double) * count, cudaMemcpyDeviceToHost, stream_), "D2H allreduce");
+  sync();
+  if (host_ar_(h, count, host_ar_ctx_) != 0) throw Error{4, "host all-reduce callback failed"};
+  check(cudaMemcpyAsync(dev, h, sizeof(double) * count, cudaMemcpyHostToDevice, stream_), "H2D allreduce");
+  sync();
+}
+
+void Engine::allreduce_host(double* host, int64_t count) {
+  if (world_ == 1 || count <= 0) return;
+  if (nccl_comm_) {
+    reserve(d_tmp_, sizeof(double) * count);
+    check(cudaMemcpyAsync(d_tmp_.p, host, sizeof(double) * count, cudaMemcpyHostToDevice, stream_), "H2D");
+    allreduce((double*)d_tmp_.p, count);
+    check(cudaMemcpyAsync(host, d_tmp_.p, sizeof(double) * count, cudaMemcpyDeviceToHost, stream_), "D2H");
+    sync();
+    return;
+  }
+  if (host_ar_(host, count, host_ar_ctx_) != 0) throw Error{4, "host all-reduce callback failed"};
+}
+
+// ------------------------------------------------------------------- data ---
+// Rows travel host -> device through two staging slots so that the copy of
+// block i+1 overlaps the conversion kernel of block i.  Row-major blocks in
+// page-locked caller memory are copied straight from the caller's buffer.
+template <typename T>
+void Engine::upload_rows(View& v, const double* const* X, const int64_t* Nj, const int64_t* ld, int J, int layout,
+                         const std::vector<double>& mean) {
+  const int D = v.D;
+  reserve(d_mean_, sizeof(double) * D);
+  double* d_mean = (double*)d_mean_.p;
+  check(cudaMemcpyAsync(d_mean, mean.data(), sizeof(double) * D, cudaMemcpyHostToDevice, stream_), "H2D mean");
+  const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(64u << 20) / (8 * (int64_t)D));
+  const size_t slot_bytes = sizeof(double) * chunk_rows * D;
+  void* d_stage[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  double* h = (double*)pinned(2 * slot_bytes);
+  auto cleanup = [&]() {
+    for (int i = 0; i < 2; ++i) {
+      if (d_stage[i]) cudaFree(d_stage[i]);
+      if (done[i]) cudaEventDestroy(done[i]);
+    }
+  };
+  try {
+    for (int i = 0; i < 2; ++i) {
+      dev_alloc(&d_stage[i], slot_bytes);
+      check(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming), "event");
+    }
+    int64_t row0 = 0;
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (int j = 0; j < J; ++j) {
+      const int64_t ldj = ld ? ld[j] : (layout == 0 ? D : Nj[j]);
+      bool pinned_src = false;
+      if (Nj[j] > 0 && layout == 0 && ldj == D) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, X[j]) == cudaSuccess) pinned_src = at.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+      }
+      for (int64_t r = 0; r < Nj[j]; r += chunk_rows) {
+        const int64_t rows = std::min(chunk_rows, Nj[j] - r);
+        if (used[slot]) check(cudaEventSynchronize(done[slot]), "event sync");
+        const double* src;
+        if (pinned_src) {
+          src = X[j] + r * ldj;
+        } else {
+          double* hs = h + (size_t)slot * chunk_rows * D;
+          if (layout == 0) {
+            if (ldj == D) std::memcpy(hs, X[j] + r * ldj, sizeof(double) * rows * D);
+            else for (int64_t n = 0; n < rows; ++n) std::memcpy(hs + n * D, X[j] + (r + n) * ldj, sizeof(double) * D);
+          } else {
+            for (int d = 0; d < D; ++d) std::memcpy(hs + (int64_t)d * rows, X[j] + (int64_t)d * ldj + r, sizeof(double) * rows);
+          }
+          src = hs;
+        }
+        check(cudaMemcpyAsync(d_stage[slot], src, sizeof(double) * rows * D, cudaMemcpyHostToDevice, stream_), "H2D rows");
+        check(dev::convert_rows<T>(stream_, (const double*)d_stage[slot], rows, D, layout == 0 ? D : rows, layout != 0,
+                                   d_mean, (T*)v.X + (row0 + r) * v.ldx, v.ldx),
+              "convert_rows");
+        check(cudaEventRecord(done[slot], stream_), "event record");
+        used[slot] = true;
+        slot ^= 1;
+      }
+      row0 += Nj[j];
+    }
+    sync();
+  } catch (...) {
+    cudaStreamSynchronize(stream_);
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
+void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int D, const int64_t* ld, int layout) {
+  if (J < 1 || D < 1 || X == nullptr || Nj == nullptr) throw_invalid("set_data: bad arguments");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  free_view(main_);
+  int64_t N = 0;
+  for (int j = 0; j < J; ++j) {
+    if (Nj[j] < 0 || (Nj[j] > 0 && X[j] == nullptr)) throw_invalid("set_data: bad group");
+    N += Nj[j];
+  }
+  Nj_.assign(Nj, Nj + J);
+  // Centre subtracted at upload: the column mean of (at most) the first 2^20
+  // local rows, averaged over ranks.  Any vector near the data works -- it only
+  // conditions the fp32 arithmetic -- so a sample keeps large uploads one-pass.
+  std::vector<double> sums(D + 2, 0.0);
+  {
+    int64_t left = (int64_t)1 << 20;
+    for (int j = 0; j < J && left > 0; ++j) {
+      const int64_t ldj = ld ? ld[j] : (layout == 0 ? D : Nj[j]);
+      const int64_t take = std::min(left, Nj[j]);
+      for (int d = 0; d < D; ++d) {
+        double s = 0;
+        if (layout == 0) for (int64_t n = 0; n < take; ++n) s += X[j][n * ldj + d];
+        else for (int64_t n = 0; n < take; ++n) s += X[j][(int64_t)d * ldj + n];
+        sums[d] += s;
+      }
+      sums[D] += (double)take;
+      left -= take;
+    }
+  }
+  sums[D + 1] = (double)N;
+  allreduce_host(sums.data(), D + 2);
+  N_total_ = (int64_t)std::llround(sums[D + 1]);
+  centre_.assign(D, 0.0);
+  if (sums[D] > 0)
+    for (int d = 0; d < D; ++d) centre_[d] = sums[d] / sums[D];
+
+  main_.N = N;
+  main_.D = D;
+  main_.J = J;
+  main_.ldx = round_up(D, 4);
+  main_.owns_x = true;
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  dev_alloc(&main_.X, (size_t)std::max<int64_t>(N, 1) * main_.ldx * es);
+  if (J > 1) {
+    dev_alloc((void**)&main_.gid, sizeof(int32_t) * std::max<int64_t>(N, 1));
+    std::vector<int32_t> g((size_t)N);
+    int64_t o = 0;
+    for (int j = 0; j < J; ++j)
+      for (int64_t n = 0; n < Nj[j]; ++n) g[o++] = j;
+    check(cudaMemcpy(main_.gid, g.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice), "H2D gid");
+  }
+  if (prec_ == kF32) upload_rows<float>(main_, X, Nj, ld, J, layout, centre_);
+  else upload_rows<double>(main_, X, Nj, ld, J, layout, centre_);
+  clusters_.clear();
+  weights_.clear();
+  model_ = -1;
+}
+
+void Engine::set_data_device_f32(const float* X, int64_t N, int D, int64_t ld, const int32_t* gid, int J) {
+  if (N < 0 || D < 1 || ld < D || J < 1 || (J > 1 && gid == nullptr)) throw_invalid("set_data_device: bad arguments");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  free_view(main_);
+  // column sums on the device, then the mean over all ranks
+  reserve(d_tmp_, sizeof(double) * (D + 1));
+  check(cudaMemsetAsync(d_tmp_.p, 0, sizeof(double) * (D + 1), stream_), "memset");
+  check(dev::colsum_f32(stream_, X, N, D, ld, (double*)d_tmp_.p), "colsum_f32");
+  std::vector<double> sums(D + 1, 0.0);
+  check(cudaMemcpyAsync(sums.data(), d_tmp_.p, sizeof(double) * D, cudaMemcpyDeviceToHost, stream_), "D2H sums");
+  sync();
+  sums[D] = (double)N;
+  allreduce_host(sums.data(), D + 1);
+  N_total_ = (int64_t)std::llround(sums[D]);
+  centre_.assign(D, 0.0);
+  if (N_total_ > 0)
+    for (int d = 0; d < D; ++d) centre_[d] = sums[d] / sums[D];
+
+  main_.N = N;
+  main_.D = D;
+  main_.J = J;
+  main_.ldx = round_up(D, 4);
+  main_.owns_x = true;
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  dev_alloc(&main_.X, (size_t)std::max<int64_t>(N, 1) * main_.ldx * es);
+  reserve(d_tmp_, sizeof(double) * D);
+  check(cudaMemcpyAsync(d_tmp_.p, centre_.data(), sizeof(double) * D, cudaMemcpyHostToDevice, stream_), "H2D mean");
+  if (prec_ == kF32)
+    check(dev::convert_f32<float>(stream_, X, N, D, ld, (const double*)d_tmp_.p, (float*)main_.X, main_.ldx), "convert");
+  else
+    check(dev::convert_f32<double>(stream_, X, N, D, ld, (const double*)d_tmp_.p, (double*)main_.X, main_.ldx), "convert");
+  Nj_.assign(J, 0);
+  if (J > 1) {
+    dev_alloc((void**)&main_.gid, sizeof(int32_t) * std::max<int64_t>(N, 1));
+    check(cudaMemcpyAsync(main_.gid, gid, sizeof(int32_t) * N, cudaMemcpyDeviceToDevice, stream_), "D2D gid");
+    std::vector<int32_t> g((size_t)N);
+    check(cudaMemcpyAsync(g.data(), gid, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, stream_), "D2H gid");
+    sync();
+    for (int64_t n = 0; n < N; ++n) {
+      if (g[n] < 0 || g[n] >= J || (n > 0 && g[n] < g[n - 1])) throw_invalid("group ids must be non-decreasing in [0,J)");
+      Nj_[g[n]]++;
+    }
+  } else {
+    Nj_[0] = N;
+  }
+  sync();
+  clusters_.clear();
+  weights_.clear();
+  model_ = -1;
+}
+
+int64_t Engine::num_rows(int j) const {
+  if (j < 0) return main_.N;
+  if (j >= (int)Nj_.size()) return -1;
+  return Nj_[j];
+}
+
+// ------------------------------------------------------------ VB iteration --
+void Engine::group_counts(View& v, std::vector<double>& Njk) {
+  const int J = v.J, K = v.K;
+  reserve(d_stats_, sizeof(double) * (size_t)J * K);
+  double* d = (double*)d_stats_.p;
+  check(cudaMemsetAsync(d, 0, sizeof(double) * (size_t)J * K, stream_), "memset");
+  if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d), "colsum");
+  else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d), "colsum");
+  ++launches_;
+  allreduce(d, (int64_t)J * K);
+  Njk.resize((size_t)J * K);
+  check(cudaMemcpyAsync(Njk.data(), d, sizeof(double) * (size_t)J * K, cudaMemcpyDeviceToHost, stream_), "D2H Njk");
+  sync();
+}
+
+// sparse-update mask: group j contributes to / competes for cluster k only if
+// Njk >= ZEROCUTOFF (cluster.cpp:69-70, :111-112)
+void Engine::build_act(const std::vector<double>& Njk, int J, int K) {
+  act_.assign((size_t)J * K, 1);
+  if (!sparse_) {
+    act_.clear();
+    return;
+  }
+  for (size_t i = 0; i < act_.size(); ++i) act_[i] = Njk[i] >= kZeroCutoff ? 1 : 0;
+  reserve(d_act_, act_.size());
+  check(cudaMemcpyAsync(d_act_.p, act_.data(), act_.size(), cudaMemcpyHostToDevice, stream_), "H2D act");
+}
+
+void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                    const std::vector<std::vector<double>>& centres) {
+  const int J = v.J, K = v.K, D = v.D;
+  const bool full = ckind_ == kGaussWish;
+  const int64_t Sz = full ? (int64_t)D * D : D;
+  const int cld = full ? dev::full_dp(D) : D;  // leading dimension of the centre table
+  if (full && cld == 0) throw_invalid("full-covariance models support D <= 256");
+  const int64_t nJK = (int64_t)J * K, nstat = nJK + (int64_t)K * D + K * Sz;
+  reserve(d_stats_, sizeof(double) * nstat);
+  double* d_njk = (double*)d_stats_.p;
+  double* d_xs = d_njk + nJK;
+  double* d_S = d_xs + (int64_t)K * D;
+  check(cudaMemsetAsync(d_njk, 0, sizeof(double) * nstat, stream_), "memset stats");
+
+  // centres, rounded to the device type; the host un-centres with the same values
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  std::vector<double> craw((size_t)K * D);
+  {
+    unsigned char* h = (unsigned char*)pinned((size_t)K * cld * es);
+    std::memset(h, 0, (size_t)K * cld * es);
+    for (int k = 0; k < K; ++k)
+      for (int d = 0; d < D; ++d) {
+        const double rel = centres[k][d] - centre_[d];
+        double used;
+        if (prec_ == kF32) {
+          const float f = (float)rel;
+          ((float*)h)[(size_t)k * cld + d] = f;
+          used = (double)f;
+        } else {
+          ((double*)h)[(size_t)k * cld + d] = rel;
+          used = rel;
+        }
+        craw[(size_t)k * D + d] = used + centre_[d];
+      }
+    reserve(d_cen_, (size_t)K * cld * es);
+    check(cudaMemcpyAsync(d_cen_.p, h, (size_t)K * cld * es, cudaMemcpyHostToDevice, stream_), "H2D centres");
+  }
+
+  check(cudaEventRecord(ev_[0], stream_), "event");
+  if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
+  else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
+  ++launches_;
+  std::vector<double> host((size_t)nstat);
+  const uint8_t* d_act = nullptr;
+  if (sparse_) {
+    allreduce(d_njk, nJK);
+    check(cudaMemcpyAsync(host.data(), d_njk, sizeof(double) * nJK, cudaMemcpyDeviceToHost, stream_), "D2H Njk");
+    sync();
+    build_act(host, J, K);
+    d_act = (const uint8_t*)d_act_.p;
+  }
+  cudaError_t ke;
+  if (prec_ == kF32) {
+    ke = full ? dev::sstat_full<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
+                                        (const float*)d_cen_.p, d_act, d_xs, d_S)
+              : dev::sstat_diag<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
+                                        (const float*)d_cen_.p, d_act, d_xs, d_S);
+  } else {
+    ke = full ? dev::sstat_full<double>(stream_, (const double*)v.X, v.N, D, v.ldx, v.gid, (const double*)v.q, v.ldq, K,
+                                         (const double*)d_cen_.p, d_act, d_xs, d_S)
+              : dev::sstat_diag<double>(stream_, (const double*)v.X, v.N, D, v.ldx, v.gid, (const double*)v.q, v.ldq,
+                                         K, (const double*)d_cen_.p, d_act, d_xs, d_S);
+  }
+  check(ke, "sstat kernel");
+  ++launches_;
+  check(cudaEventRecord(ev_[1], stream_), "event");
+  if (sparse_) allreduce(d_xs, nstat - nJK);
+  else allreduce(d_njk, nstat);
+  check(cudaMemcpyAsync(host.data() + (sparse_ ? nJK : 0), sparse_ ? d_xs : d_njk,
+                        sizeof(double) * (sparse_ ? nstat - nJK : nstat), cudaMemcpyDeviceToHost, stream_),
+        "D2H stats");
+  sync();
+
+  const double* Njk = host.data();
+  const double* xs = Njk + nJK;
+  const double* S = xs + (int64_t)K * D;
+  for (int j = 0; j < J; ++j) weights[j].update(Njk + (int64_t)j * K, K);
+  for (int k = 0; k < K; ++k) {
+    double n = 0;
+    for (int j = 0; j < J; ++j)
+      if (act_.empty() || act_[(size_t)j * K + k]) n += Njk[(int64_t)j * K + k];
+    clusters[k].add_centred_stats(n, xs + (int64_t)k * D, S + (int64_t)k * Sz, &craw[(size_t)k * D]);
+  }
+}
+
+double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters,
+                      int mode, std::vector<double>* H) {
+  const int J = v.J, K = v.K, D = v.D;
+  const bool full = ckind_ == kGaussWish;
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  const int DP = full ? dev::full_dp(D) : D;
+  if (full && DP == 0) throw_invalid("full-covariance models support D <= 256");
+  const size_t nR = full ? (size_t)K * DP * DP : (size_t)K * D;
+  const size_t nM = (size_t)K * DP;
+  // pinned staging: [R | mhi | mlo | chat | lw]
+  const size_t total = (nR + 2 * nM + K + (size_t)J * K) * es;
+  unsigned char* h = (unsigned char*)pinned(total);
+  std::memset(h, 0, total);
+  auto put = [&](size_t off_elems, size_t idx, double val) {
+    if (prec_ == kF32) ((float*)h)[off_elems + idx] = (float)val;
+    else ((double*)h)[off_elems + idx] = val;
+  };
+  std::vector<double> cc(K);
+  double cbar = 0;
+  for (int k = 0; k < K; ++k) {
+    cc[k] = clusters[k].cconst();
+    cbar += cc[k];
+  }
+  cbar /= K;
+  if (mode == dev::kERawLogit) cbar = 0;
+  std::vector<double> R;
+  const size_t oM = nR, oL = nR + nM, oC = nR + 2 * nM, oW = oC + K;
+  for (int k = 0; k < K; ++k) {
+    clusters[k].whitener(R);
+    if (full) {
+      for (int i = 0; i < D; ++i)
+        for (int d = 0; d <= i; ++d) put(0, ((size_t)k * DP + d) * DP + i, R[(size_t)i * D + d]);
+    } else {
+      for (int d = 0; d < D; ++d) put(0, (size_t)k * D + d, R[d] * R[d]);
+    }
+    const std::vector<double>& m = clusters[k].mean();
+    for (int d = 0; d < D; ++d) {
+      const double rel = m[d] - centre_[d];
+      if (prec_ == kF32) {
+        const float hi = (float)rel;
+        ((float*)h)[oM + (size_t)k * DP + d] = hi;
+        ((float*)h)[oL + (size_t)k * DP + d] = (float)(rel - (double)hi);
+      } else {
+        ((double*)h)[oM + (size_t)k * DP + d] = rel;
+      }
+    }
+    put(oC, k, mode == dev::kERawLogit ? 0.0 : cc[k] - cbar);
+  }
+  for (int j = 0; j < J; ++j) {
+    const std::vector<double>& e = weights[j].Elogweight();
+    for (int k = 0; k < K; ++k) put(oW, (size_t)j * K + k, mode == dev::kERawLogit ? 0.0 : e[k]);
+  }
+  reserve(d_RT_, total);
+  check(cudaMemcpyAsync(d_RT_.p, h, total, cudaMemcpyHostToDevice, stream_), "H2D params");
+  unsigned char* base = (unsigned char*)d_RT_.p;
+  const void* dR = base;
+  const void* dMh = base + oM * es;
+  const void* dMl = base + oL * es;
+  const void* dC = base + oC * es;
+  const void* dW = base + oW * es;
+  const uint8_t* d_act = (sparse_ && !act_.empty() && mode != dev::kERawLogit) ? (const uint8_t*)d_act_.p : nullptr;
+
+  reserve(d_small_, sizeof(double) * (K + 2));
+  double* d_fz = (double*)d_small_.p;
+  double* d_H = d_fz + 1;
+  check(cudaMemsetAsync(d_fz, 0, sizeof(double) * (K + 1), stream_), "memset");
+  check(cudaEventRecord(ev_[2], stream_), "event");
+  cudaError_t ke;
+  if (prec_ == kF32) {
+    ke = full ? dev::estep_full<float>(stream_, sms_, (const float*)v.X, v.N, D, v.ldx, v.gid, K, (const float*)dR,
+                                        (const float*)dMh, (const float*)dMl, (const float*)dC, (const float*)dW, d_act,
+                                        (float*)v.q, v.ldq, mode, d_fz, d_H)
+              : dev::estep_diag<float>(stream_, sms_, (const float*)v.X, v.N, D, v.ldx, v.gid, K, (const float*)dR,
+                                        (const float*)dMh, (const float*)dMl, (const float*)dC, (const float*)dW, d_act,
+                                        (float*)v.q, v.ldq, mode, d_fz, d_H);
+  } else {
+    ke = full ? dev::estep_full<double>(stream_, sms_, (const double*)v.X, v.N, D, v.ldx, v.gid, K, (const double*)dR,
+                                         (const double*)dMh, (const double*)dMl, (const double*)dC, (const double*)dW,
+                                         d_act, (double*)v.q, v.ldq, mode, d_fz, d_H)
+              : dev::estep_diag<double>(stream_, sms_, (const double*)v.X, v.N, D, v.ldx, v.gid, K, (const double*)dR,
+                                         (const double*)dMh, (const double*)dMl, (const double*)dC, (const double*)dW,
+                                         d_act, (double*)v.q, v.ldq, mode, d_fz, d_H);
+  }
+  if (ke == cudaErrorInvalidValue) throw_invalid("unsupported (D, K) for the E-step kernel at this precision");
+  check(ke, "estep kernel");
+  ++launches_;
+  check(cudaEventRecord(ev_[3], stream_), "event");
+  if (mode == dev::kERawLogit) return 0.0;
+  allreduce(d_fz, K + 1);
+  std::vector<double> out(K + 1);
+  check(cudaMemcpyAsync(out.data(), d_fz, sizeof(double) * (K + 1), cudaMemcpyDeviceToHost, stream_), "D2H Fz");
+  sync();
+  if (H) {
+    H->assign(out.begin() + 1, out.end());
+    H->push_back(cbar);  // caller adds cbar * Nk
+  }
+  return -(out[0] + (double)v_ntot_ * cbar);
+}
+
+void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                       std::vector<std::vector<double>>& hints, double* F) {
+  const int K = v.K, D = v.D;
+  std::vector<std::vector<double>> centres(K);
+  for (int k = 0; k < K; ++k) {
+    const bool have_hint = k < (int)hints.size() && (int)hints[k].size() == D;
+    if (hints_first_ && have_hint) centres[k] = hints[k];
+    else if (clusters[k].getN() > 0) centres[k] = clusters[k].mean();
+    else if (have_hint) centres[k] = hints[k];
+    else centres[k] = centre_;
+  }
+  hints_first_ = false;
+  for (int k = 0; k < K; ++k) clusters[k].clearobs();
+  sphase(v, weights, clusters, centres);
+  for (int k = 0; k < K; ++k) clusters[k].update();
+  const double Fz = ephase(v, weights, clusters, dev::kEWrite, nullptr);
+  double Fw = 0, Fc = 0;
+  for (size_t j = 0; j < weights.size(); ++j) Fw += weights[j].fenergy();
+  for (int k = 0; k < K; ++k) Fc += clusters[k].fenergy();
+  *F = Fc + Fw + Fz;
+}
+
+double Engine::vbem(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                    std::vector<std::vector<double>>& hints, int maxit, bool record, int* iters) {
+  const int J = v.J, K = v.K;
+  while ((int)weights.size() < J) weights.emplace_back(wkind_, -1.0);  // weights.resize(J, W()), cluster.cpp:192
+  weights.resize(J, WeightPost(wkind_, -1.0));
+  while ((int)clusters.size() > K) clusters.pop_back();
+  while ((int)clusters.size() < K) clusters.emplace_back(ckind_, prior_, v.D);  // :193
+  hints.resize(K);
+  double F = DBL_MAX, Fold;
+  int i = 0, n = 0;
+  do {
+    Fold = F;
+    iteration(v, weights, clusters, hints, &F);
+    ++n;
+    if (record) {
+      trace_F_.push_back(F);
+      trace_K_.push_back(K);
+    }
+    if ((F - Fold) / std::fabs(Fold) > kFengyDel) throw_runtime("Free energy increase!");
+    if (verbose_) std::cout << '-' << std::flush;
+  } while ((std::fabs((Fold - F) / Fold) > kConverge) && ((i++ < maxit) || (maxit < 0)));
+  if (iters) *iters = n;
+  return F;
+}
+
+bool Engine::prune(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters) {
+  const int K = (int)clusters.size();
+  std::vector<int32_t> keep;
+  for (int k = 0; k < K; ++k)
+    if (!(clusters[k].getN() < kZeroCutoff)) keep.push_back(k);
+  if ((int)keep.size() == K) return false;
+  if (verbose_) std::cout << '*' << std::flush;
+  std::vector<ClusterPost> nc;
+  std::vector<std::vector<double>> nh;
+  for (int32_t k : keep) {
+    nc.push_back(clusters[k]);
+    nh.push_back(k < (int)hints_.size() ? hints_[k] : std::vector<double>());
+  }
+  clusters.swap(nc);
+  if (&clusters == &clusters_) hints_.swap(nh);
+  const int newK = (int)keep.size();
+  reserve(d_tmp_, sizeof(int32_t) * std::max(newK, 1));
+  if (newK > 0)
+    check(cudaMemcpyAsync(d_tmp_.p, keep.data(), sizeof(int32_t) * newK, cudaMemcpyHostToDevice, stream_), "H2D keep");
+  if (prec_ == kF32) check(dev::prune_columns<float>(stream_, (float*)v.q, v.ldq, v.N, (const int32_t*)d_tmp_.p, newK), "prune");
+  else check(dev::prune_columns<double>(stream_, (double*)v.q, v.ldq, v.N, (const int32_t*)d_tmp_.p, newK), "prune");
+  v.K = newK;
+  std::vector<double> Njk;
+  group_counts(v, Njk);
+  for (int j = 0; j < v.J; ++j) weights[j].update(Njk.data() + (size_t)j * newK, newK);
+  return true;
+}
+
+namespace {
+struct GreedOrder {
+  int k, tally;
+  double Fk;
+};
+// comutils.h:60-68
+bool greedcomp(const GreedOrder& i, const GreedOrder& j) {
+  if (i.tally == j.tally) return i.Fk > j.Fk;
+  return i.tally < j.tally;
+}
+bool anyempty(const std::vector<ClusterPost>& c) {  // comutils.h:114-123
+  for (const auto& x : c)
+    if (x.getN() <= 1) return true;
+  return false;
+}
+}  // namespace
+
+bool Engine::split_gr(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                      std::vector<int>& tally, double F, int maxclusters) {
+  const int K = (int)clusters.size(), D = v.D, J = v.J;
+  if (K >= maxclusters && maxclusters >= 0) return false;
+  tally.resize(K, 0);
+
+  // rank clusters by their approximate free-energy contribution (cluster.cpp:386-418)
+  std::vector<double> H, Njk;
+  v_ntot_ = N_total_;
+  ephase(v, weights, clusters, dev::kEScore, &H);
+  const double cbar = H.back();
+  group_counts(v, Njk);
+  std::vector<GreedOrder> ord(K);
+  for (int k = 0; k < K; ++k) {
+    double nk = 0;
+    for (int j = 0; j < J; ++j) nk += Njk[(size_t)j * K + k];
+    ord[k].k = k;
+    ord[k].tally = tally[k];
+    ord[k].Fk = clusters[k].fenergy() - (H[k] + cbar * nk);
+  }
+  std::sort(ord.begin(), ord.end(), greedcomp);
+
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  for (const GreedOrder& cand : ord) {
+    const int k = cand.k;
+    ++tally[k];
+    if (clusters[k].getN() < 4) continue;
+
+    // members of cluster k (q > 0.5), gathered in order (partobs, comutils.cpp:56-72)
+    const int64_t nblocks = (v.N + 1023) / 1024;
+    reserve(d_tmp_, sizeof(int32_t) * (size_t)std::max<int64_t>(nblocks, 1) + 64);
+    int32_t* d_cnt = (int32_t*)d_tmp_.p;
+    reserve(d_small_, sizeof(double) * (K + 4));
+    int64_t* d_total = (int64_t*)d_small_.p;
+    int64_t M = 0;
+    if (v.N > 0) {
+      if (prec_ == kF32) check(dev::member_counts<float>(stream_, (const float*)v.q, v.ldq, v.N, k, d_cnt), "member_counts");
+      else check(dev::member_counts<double>(stream_, (const double*)v.q, v.ldq, v.N, k, d_cnt), "member_counts");
+      check(dev::scan_counts(stream_, d_cnt, nblocks, d_total), "scan_counts");
+      check(cudaMemcpyAsync(&M, d_total, sizeof(int64_t), cudaMemcpyDeviceToHost, stream_), "D2H M");
+      sync();
+    }
+    View sub;
+    sub.N = M;
+    sub.D = D;
+    sub.ldx = v.ldx;
+    sub.J = J;
+    sub.owns_x = true;
+    void* d_map = nullptr;
+    struct Guard {
+      Engine* e; View* s; void** map;
+      ~Guard() { if (*map) cudaFree(*map); e->free_view(*s); }
+    } guard{this, &sub, &d_map};
+    dev_alloc(&sub.X, (size_t)std::max<int64_t>(M, 1) * sub.ldx * es);
+    if (J > 1) dev_alloc((void**)&sub.gid, sizeof(int32_t) * std::max<int64_t>(M, 1));
+    dev_alloc(&d_map, sizeof(int64_t) * std::max<int64_t>(M, 1));
+    ensure_q(sub, 2);
+    sub.K = 2;
+    if (v.N > 0) {
+      if (prec_ == kF32)
+        check(dev::gather_members<float>(stream_, (const float*)v.q, v.ldq, v.N, k, d_cnt, (const float*)v.X, v.ldx, D,
+                                         v.gid, (float*)sub.X, sub.gid, (int64_t*)d_map), "gather");
+      else
+        check(dev::gather_members<double>(stream_, (const double*)v.q, v.ldq, v.N, k, d_cnt, (const double*)v.X, v.ldx,
+                                          D, v.gid, (double*)sub.X, sub.gid, (int64_t*)d_map), "gather");
+    }
+    // initial hard split perpendicular to the principal axis (splitobs)
+    std::vector<double> dir;
+    clusters[k].split_direction(dir);
+    const std::vector<double>& mk = clusters[k].mean();
+    {
+      unsigned char* h = (unsigned char*)pinned(2 * (size_t)D * es);
+      for (int d = 0; d < D; ++d) {
+        if (prec_ == kF32) {
+          ((float*)h)[d] = (float)(mk[d] - centre_[d]);
+          ((float*)h)[D + d] = (float)dir[d];
+        } else {
+          ((double*)h)[d] = mk[d] - centre_[d];
+          ((double*)h)[D + d] = dir[d];
+        }
+      }
+      reserve(d_cen_, 2 * (size_t)D * es);
+      check(cudaMemcpyAsync(d_cen_.p, h, 2 * (size_t)D * es, cudaMemcpyHostToDevice, stream_), "H2D split dir");
+    }
+    unsigned long long* d_sc = (unsigned long long*)((char*)d_small_.p + 16);
+    check(cudaMemsetAsync(d_sc, 0, sizeof(unsigned long long), stream_), "memset");
+    if (prec_ == kF32)
+      check(dev::split_side<float>(stream_, (const float*)sub.X, M, D, sub.ldx, (const float*)d_cen_.p,
+                                   (const float*)d_cen_.p + D, (float*)sub.q, sub.ldq, d_sc), "split_side");
+    else
+      check(dev::split_side<double>(stream_, (const double*)sub.X, M, D, sub.ldx, (const double*)d_cen_.p,
+                                    (const double*)d_cen_.p + D, (double*)sub.q, sub.ldq, d_sc), "split_side");
+    unsigned long long sc = 0;
+    check(cudaMemcpyAsync(&sc, d_sc, sizeof(sc), cudaMemcpyDeviceToHost, stream_), "D2H scount");
+    sync();
+    double cnts[2] = {(double)sc, (double)M};
+    allreduce_host(cnts, 2);
+    const int64_t scount = (int64_t)std::llround(cnts[0]), Mtot = (int64_t)std::llround(cnts[1]);
+    if (scount < 2 || scount > Mtot - 2) continue;
+
+    // refine the split on the members only (cluster.cpp:460-465)
+    std::vector<WeightPost> wspl;
+    std::vector<ClusterPost> cspl;
+    std::vector<std::vector<double>> hspl(2, mk);
+    v_ntot_ = Mtot;
+    hints_first_ = true;
+    vbem(sub, wspl, cspl, hspl, kSplitIter, true, nullptr);
+    if (anyempty(cspl)) continue;
+
+    // augment the labels of the whole data set (auglabels, comutils.cpp:75-104)
+    ensure_q(v, K + 1);
+    if (prec_ == kF32) {
+      check(dev::copy_q<float>(stream_, (const float*)v.q, (float*)v.q2, v.ldq, v.ldq, v.N, K, K + 1), "copy_q");
+      check(dev::aug_labels<float>(stream_, (const float*)sub.q, sub.ldq, (const int64_t*)d_map, M, (const float*)v.q,
+                                   (float*)v.q2, v.ldq, k, K), "aug_labels");
+    } else {
+      check(dev::copy_q<double>(stream_, (const double*)v.q, (double*)v.q2, v.ldq, v.ldq, v.N, K, K + 1), "copy_q");
+      check(dev::aug_labels<double>(stream_, (const double*)sub.q, sub.ldq, (const int64_t*)d_map, M,
+                                    (const double*)v.q, (double*)v.q2, v.ldq, k, K), "aug_labels");
+    }
+    swap_q(v);  // v.q = augmented labels, v.q2 = the labels we may have to go back to
+    v.K = K + 1;
+    std::vector<std::vector<double>> haug(K + 1);
+    for (int i = 0; i < K; ++i) haug[i] = clusters[i].mean();
+    haug[K] = cspl[1].mean();
+    std::vector<double> new_hint = haug[K];
+    v_ntot_ = N_total_;
+    hints_first_ = true;
+    double Fsplit;
+    try {
+      Fsplit = vbem(v, wspl, cspl, haug, 1, true, nullptr);
+    } catch (...) {
+      swap_q(v);
+      v.K = K;
+      throw;
+    }
+    bool accept = !anyempty(cspl);
+    if (accept && verbose_) std::cout << '=' << std::flush;
+    accept = accept && (Fsplit < F) && (std::fabs((F - Fsplit) / F) > kConverge);
+    if (accept) {
+      tally[k] = 0;
+      if (&clusters == &clusters_) {
+        hints_.resize(K + 1);
+        hints_[K] = new_hint;
+      }
+      return true;
+    }
+    swap_q(v);
+    v.K = K;
+  }
+  return false;
+}
+
+// ------------------------------------------------------------ public fits ---
+void Engine::model_init(int model, double prior, double wprior, bool sparse) {
+  if (main_.X == nullptr) throw_invalid("no observations loaded (call lcb_set_data first)");
+  model_kinds(model, &wkind_, &ckind_);
+  if (!(prior > 0)) throw_invalid("clustwidth must be > 0!");
+  model_ = model;
+  prior_ = prior;
+  wprior_ = wprior;
+  sparse_ = sparse;
+  weights_.clear();
+  clusters_.clear();
+  hints_.clear();
+  act_.clear();
+  for (int j = 0; j < main_.J; ++j) weights_.emplace_back(wkind_, wprior_);
+  trace_F_.clear();
+  trace_K_.clear();
+  main_.K = 0;
+}
+
+void Engine::learn(int model, double prior, double wprior, int maxclusters, bool sparse, bool verbose,
+                   unsigned nthreads, double* F, int* K) {
+  if (nthreads < 1) throw_invalid("Must specify at least one thread for execution!");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  model_init(model, prior, wprior, sparse);
+  verbose_ = verbose;
+  ensure_q(main_, 1);
+  if (prec_ == kF32) check(dev::fill_ones<float>(stream_, (float*)main_.q, main_.ldq, main_.N), "fill_ones");
+  else check(dev::fill_ones<double>(stream_, (double*)main_.q, main_.ldq, main_.N), "fill_ones");
+  main_.K = 1;
+  std::vector<int> tally;
+  bool issplit = true;
+  double Fcur = 0;
+  while (issplit) {
+    v_ntot_ = N_total_;
+    Fcur = vbem(main_, weights_, clusters_, hints_, -1, true, nullptr);
+    prune(main_, weights_, clusters_);
+    if (verbose_) std::cout << '<' << std::flush;
+    issplit = split_gr(main_, weights_, clusters_, tally, Fcur, maxclusters);
+    if (verbose_) std::cout << '>' << std::endl;
+  }
+  if (verbose_) {
+    std::cout << "Finished!" << std::endl;
+    std::cout << "Number of clusters = " << clusters_.size() << std::endl;
+    std::cout << "Free energy = " << Fcur << std::endl;
+  }
+  last_F_ = Fcur;
+  if (F) *F = Fcur;
+  if (K) *K = (int)clusters_.size();
+}
+
+void Engine::set_qz(const double* q0, int K) {
+  if (model_ < 0) throw_invalid("call lcb_model_init first");
+  if (K < 1 || q0 == nullptr) throw_invalid("set_qz: bad arguments");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  main_.K = 0;
+  ensure_q(main_, K);
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (8 * (int64_t)K));
+  reserve(d_tmp_, sizeof(double) * chunk * K);
+  double* h = (double*)pinned(sizeof(double) * chunk * K);
+  for (int64_t r = 0; r < main_.N; r += chunk) {
+    const int64_t rows = std::min(chunk, main_.N - r);
+    std::memcpy(h, q0 + r * K, sizeof(double) * rows * K);
+    check(cudaMemcpyAsync(d_tmp_.p, h, sizeof(double) * rows * K, cudaMemcpyHostToDevice, stream_), "H2D q0");
+    if (prec_ == kF32)
+      check(dev::q_from_double<float>(stream_, (const double*)d_tmp_.p, rows, K, (float*)main_.q + r * main_.ldq, main_.ldq), "q_from_double");
+    else
+      check(dev::q_from_double<double>(stream_, (const double*)d_tmp_.p, rows, K, (double*)main_.q + r * main_.ldq, main_.ldq), "q_from_double");
+    sync();
+  }
+  main_.K = K;
+  clusters_.clear();
+  hints_.clear();
+}
+
+void Engine::set_labels_device(const int32_t* labels, int K) {
+  if (model_ < 0) throw_invalid("call lcb_model_init first");
+  if (K < 1 || labels == nullptr) throw_invalid("set_labels: bad arguments");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  main_.K = 0;
+  ensure_q(main_, K);
+  if (prec_ == kF32) check(dev::labels_to_q<float>(stream_, labels, (float*)main_.q, main_.ldq, main_.N, K), "labels_to_q");
+  else check(dev::labels_to_q<double>(stream_, labels, (double*)main_.q, main_.ldq, main_.N, K), "labels_to_q");
+  sync();
+  main_.K = K;
+  clusters_.clear();
+  hints_.clear();
+}
+
+void Engine::vbem_public(int maxit, double* F, int* iters) {
+  if (model_ < 0 || main_.K < 1) throw_invalid("model and responsibilities must be set first");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  trace_F_.clear();
+  trace_K_.clear();
+  v_ntot_ = N_total_;
+  last_F_ = vbem(main_, weights_, clusters_, hints_, maxit, true, iters);
+  if (F) *F = last_F_;
+}
+
+void Engine::vbem_step(double* F) {
+  if (model_ < 0 || main_.K < 1) throw_invalid("model and responsibilities must be set first");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  const int J = main_.J, K = main_.K;
+  while ((int)weights_.size() < J) weights_.emplace_back(wkind_, -1.0);
+  while ((int)clusters_.size() > K) clusters_.pop_back();
+  while ((int)clusters_.size() < K) clusters_.emplace_back(ckind_, prior_, main_.D);
+  hints_.resize(K);
+  v_ntot_ = N_total_;
+  const long l0 = launches_;
+  cudaEvent_t a, b;
+  check(cudaEventCreate(&a), "event");
+  check(cudaEventCreate(&b), "event");
+  check(cudaEventRecord(a, stream_), "event");
+  double f;
+  iteration(main_, weights_, clusters_, hints_, &f);
+  check(cudaEventRecord(b, stream_), "event");
+  sync();
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
+  t_s_ = ms;
+  cudaEventElapsedTime(&ms, ev_[2], ev_[3]);
+  t_e_ = ms;
+  cudaEventElapsedTime(&ms, a, b);
+  t_all_ = ms;
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  step_launches_ = launches_ - l0;
+  last_F_ = f;
+  if (F) *F = f;
+}
+
+void Engine::get_step_timing(double out[4]) {
+  out[0] = t_s_;
+  out[1] = t_e_;
+  out[2] = t_all_;
+  out[3] = (double)step_launches_;
+}
+
+// ---------------------------------------------------------------- results ---
+void Engine::get_qz(int j, double* out, int64_t ld, int layout) {
+  if (j < 0 || j >= main_.J || out == nullptr) throw_invalid("get_qz: bad group");
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  const int K = main_.K;
+  int64_t off = 0;
+  for (int g = 0; g < j; ++g) off += Nj_[g];
+  const int64_t Nj = Nj_[j];
+  if (ld < (layout == 0 ? K : Nj)) throw_invalid("get_qz: leading dimension too small");
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (8 * (int64_t)std::max(K, 1)));
+  reserve(d_tmp_, sizeof(double) * chunk * K);
+  double* h = (double*)pinned(sizeof(double) * chunk * K);
+  for (int64_t r = 0; r < Nj; r += chunk) {
+    const int64_t rows = std::min(chunk, Nj - r);
+    if (prec_ == kF32)
+      check(dev::q_to_double<float>(stream_, (const float*)main_.q + (off + r) * main_.ldq, main_.ldq, rows, K,
+                                    (double*)d_tmp_.p, K, 0), "q_to_double");
+    else
+      check(dev::q_to_double<double>(stream_, (const double*)main_.q + (off + r) * main_.ldq, main_.ldq, rows, K,
+                                     (double*)d_tmp_.p, K, 0), "q_to_double");
+    check(cudaMemcpyAsync(h, d_tmp_.p, sizeof(double) * rows * K, cudaMemcpyDeviceToHost, stream_), "D2H q");
+    sync();
+    for (int64_t n = 0; n < rows; ++n)
+      for (int k = 0; k < K; ++k) {
+        if (layout == 0) out[(r + n) * ld + k] = h[n * K + k];
+        else out[(int64_t)k * ld + r + n] = h[n * K + k];
+      }
+  }
+}
+
+void Engine::get_group_weights(int j, double* Nk, double* Elogw, double* fen) {
+  if (j < 0 || j >= (int)weights_.size()) throw_invalid("get_group_weights: bad group");
+  const WeightPost& w = weights_[j];
+  if (Nk) std::copy(w.getNk().begin(), w.getNk().end(), Nk);
+  if (Elogw) std::copy(w.Elogweight().begin(), w.Elogweight().end(), Elogw);
+  if (fen) *fen = w.fenergy();
+}
+
+void Engine::get_cluster(int k, double* N_s, double* x_s, double* xx_s, double* N, double* mean, double* cov,
+                         double* fen) {
+  if (k < 0 || k >= (int)clusters_.size()) throw_invalid("get_cluster: bad cluster");
+  const ClusterPost& c = clusters_[k];
+  if (N_s) *N_s = c.N_s();
+  if (x_s) std::copy(c.x_s().begin(), c.x_s().end(), x_s);
+  if (xx_s) std::copy(c.xx_s().begin(), c.xx_s().end(), xx_s);
+  if (N) *N = c.getN();
+  if (mean) std::copy(c.mean().begin(), c.mean().end(), mean);
+  if (cov) {
+    std::vector<double> cv = c.cov();
+    std::copy(cv.begin(), cv.end(), cov);
+  }
+  if (fen) *fen = c.fenergy();
+}
+
+// -------------------------------------------------------- operator surface ---
+namespace {
+std::vector<double> host_colmean(const double* X, int64_t N, int D, int64_t ld, int layout) {
+  std::vector<double> m(D, 0.0);
+  if (N <= 0) return m;
+  for (int d = 0; d < D; ++d) {
+    double s = 0;
+    if (layout == 0) for (int64_t n = 0; n < N; ++n) s += X[n * ld + d];
+    else for (int64_t n = 0; n < N; ++n) s += X[(int64_t)d * ld + n];
+    m[d] = s / (double)N;
+  }
+  return m;
+}
+}  // namespace
+
+void Engine::op_addobs(ClusterPost& c, const double* qk, const double* X, int64_t N, int64_t ld, int layout) {
+  const int D = c.dim();
+  if (N < 0 || (N > 0 && (X == nullptr || qk == nullptr))) throw_invalid("addobs: bad arguments");
+  if (N == 0) return;
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  // temporary view with its own centring; engine state is saved and restored
+  View saved = main_;
+  std::vector<double> saved_centre = centre_;
+  const int saved_ck = ckind_, saved_wk = wkind_;
+  const bool saved_sparse = sparse_;
+  std::vector<uint8_t> saved_act = act_;
+  main_ = View();
+  View tmp;
+  try {
+    centre_ = host_colmean(X, N, D, ld, layout);
+    tmp.N = N; tmp.D = D; tmp.J = 1; tmp.ldx = round_up(D, 4); tmp.owns_x = true;
+    const size_t es = prec_ == kF32 ? 4 : 8;
+    dev_alloc(&tmp.X, (size_t)N * tmp.ldx * es);
+    const double* Xs[1] = {X};
+    const int64_t Ns[1] = {N};
+    const int64_t lds[1] = {ld};
+    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    ensure_q(tmp, 1);
+    tmp.K = 1;
+    const int64_t chunk = 1 << 20;
+    reserve(d_tmp_, sizeof(double) * std::min(chunk, N));
+    double* h = (double*)pinned(sizeof(double) * std::min(chunk, N));
+    for (int64_t r = 0; r < N; r += chunk) {
+      const int64_t rows = std::min(chunk, N - r);
+      std::memcpy(h, qk + r, sizeof(double) * rows);
+      check(cudaMemcpyAsync(d_tmp_.p, h, sizeof(double) * rows, cudaMemcpyHostToDevice, stream_), "H2D qk");
+      if (prec_ == kF32) check(dev::q_from_double<float>(stream_, (const double*)d_tmp_.p, rows, 1, (float*)tmp.q + r * tmp.ldq, tmp.ldq), "q");
+      else check(dev::q_from_double<double>(stream_, (const double*)d_tmp_.p, rows, 1, (double*)tmp.q + r * tmp.ldq, tmp.ldq), "q");
+      sync();
+    }
+    ckind_ = c.kind();
+    sparse_ = false;
+    act_.clear();
+    std::vector<WeightPost> w(1, WeightPost(kDirichlet, -1.0));
+    std::vector<ClusterPost> cl(1, ClusterPost(c.kind(), c.getprior(), D));
+    std::vector<std::vector<double>> cen(1, c.getN() > 0 ? c.mean() : centre_);
+    const int sw = world_;
+    world_ = 1;  // operator calls are local
+    try {
+      sphase(tmp, w, cl, cen);
+    } catch (...) {
+      world_ = sw;
+      throw;
+    }
+    world_ = sw;
+    c.add_stats(cl[0].N_s(), cl[0].x_s().data(), cl[0].xx_s().data());
+  } catch (...) {
+    free_view(tmp);
+    main_ = saved; centre_ = saved_centre; ckind_ = saved_ck; wkind_ = saved_wk; sparse_ = saved_sparse; act_ = saved_act;
+    throw;
+  }
+  free_view(tmp);
+  main_ = saved; centre_ = saved_centre; ckind_ = saved_ck; wkind_ = saved_wk; sparse_ = saved_sparse; act_ = saved_act;
+}
+
+void Engine::op_eloglike(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, double* out) {
+  const int D = c.dim();
+  if (N < 0 || (N > 0 && (X == nullptr || out == nullptr))) throw_invalid("Eloglike: bad arguments");
+  if (N == 0) return;
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  View saved = main_;
+  std::vector<double> saved_centre = centre_;
+  const int saved_ck = ckind_;
+  const bool saved_sparse = sparse_;
+  main_ = View();
+  View tmp;
+  auto restore = [&]() { free_view(tmp); main_ = saved; centre_ = saved_centre; ckind_ = saved_ck; sparse_ = saved_sparse; };
+  try {
+    centre_ = c.mean();  // centre on the cluster: the device sees x - m directly
+    tmp.N = N; tmp.D = D; tmp.J = 1; tmp.ldx = round_up(D, 4); tmp.owns_x = true;
+    const size_t es = prec_ == kF32 ? 4 : 8;
+    dev_alloc(&tmp.X, (size_t)N * tmp.ldx * es);
+    const double* Xs[1] = {X};
+    const int64_t Ns[1] = {N};
+    const int64_t lds[1] = {ld};
+    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    ensure_q(tmp, 1);
+    tmp.K = 1;
+    ckind_ = c.kind();
+    sparse_ = false;
+    std::vector<WeightPost> w(1, WeightPost(kDirichlet, -1.0));
+    std::vector<ClusterPost> cl(1, c);
+    v_ntot_ = N;
+    ephase(tmp, w, cl, dev::kERawLogit, nullptr);
+    const double cc = c.cconst();
+    const int64_t chunk = 1 << 20;
+    reserve(d_tmp_, sizeof(double) * std::min(chunk, N));
+    double* h = (double*)pinned(sizeof(double) * std::min(chunk, N));
+    for (int64_t r = 0; r < N; r += chunk) {
+      const int64_t rows = std::min(chunk, N - r);
+      if (prec_ == kF32) check(dev::q_to_double<float>(stream_, (const float*)tmp.q + r * tmp.ldq, tmp.ldq, rows, 1, (double*)d_tmp_.p, 1, 0), "q");
+      else check(dev::q_to_double<double>(stream_, (const double*)tmp.q + r * tmp.ldq, tmp.ldq, rows, 1, (double*)d_tmp_.p, 1, 0), "q");
+      check(cudaMemcpyAsync(h, d_tmp_.p, sizeof(double) * rows, cudaMemcpyDeviceToHost, stream_), "D2H");
+      sync();
+      for (int64_t n = 0; n < rows; ++n) out[r + n] = cc + h[n];
+    }
+  } catch (...) {
+    restore();
+    throw;
+  }
+  restore();
+}
+
+void Engine::op_splitobs(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, uint8_t* out) {
+  const int D = c.dim();
+  if (N < 0 || (N > 0 && (X == nullptr || out == nullptr))) throw_invalid("splitobs: bad arguments");
+  if (N == 0) return;
+  check(cudaSetDevice(device_), "cudaSetDevice");
+  View tmp;
+  void* d_flags = nullptr;
+  try {
+    std::vector<double> ctr = c.mean();
+    tmp.N = N; tmp.D = D; tmp.J = 1; tmp.ldx = round_up(D, 4); tmp.owns_x = true;
+    const size_t es = prec_ == kF32 ? 4 : 8;
+    dev_alloc(&tmp.X, (size_t)N * tmp.ldx * es);
+    const double* Xs[1] = {X};
+    const int64_t Ns[1] = {N};
+    const int64_t lds[1] = {ld};
+    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, ctr);
+    else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, ctr);
+    std::vector<double> dir;
+    c.split_direction(dir);
+    unsigned char* h = (unsigned char*)pinned(2 * (size_t)D * es);
+    for (int d = 0; d < D; ++d) {
+      if (prec_ == kF32) { ((float*)h)[d] = 0.f; ((float*)h)[D + d] = (float)dir[d]; }
+      else { ((double*)h)[d] = 0.0; ((double*)h)[D + d] = dir[d]; }
+    }
+    reserve(d_cen_, 2 * (size_t)D * es);
+    check(cudaMemcpyAsync(d_cen_.p, h, 2 * (size_t)D * es, cudaMemcpyHostToDevice, stream_), "H2D dir");
+    dev_alloc(&d_flags, (size_t)N);
+    if (prec_ == kF32)
+      check(dev::side_flags<float>(stream_, (const float*)tmp.X, N, D, tmp.ldx, (const float*)d_cen_.p, (const float*)d_cen_.p + D, (uint8_t*)d_flags), "side_flags");
+    else
+      check(dev::side_flags<double>(stream_, (const double*)tmp.X, N, D, tmp.ldx, (const double*)d_cen_.p, (const double*)d_cen_.p + D, (uint8_t*)d_flags), "side_flags");
+    check(cudaMemcpyAsync(out, d_flags, (size_t)N, cudaMemcpyDeviceToHost, stream_), "D2H flags");
+    sync();
+  } catch (...) {
+    if (d_flags) cudaFree(d_flags);
+    free_view(tmp);
+    throw;
+  }
+  cudaFree(d_flags);
+  free_view(tmp);
+}
+
+}  // namespace lcb

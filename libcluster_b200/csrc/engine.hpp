@@ -1,0 +1,145 @@
+// engine.hpp -- host control flow of the VB fit over device-resident data.
+//
+// Mirrors src/cluster.cpp of the reference (vbem :177-239, split_gr :367-495,
+// prune_clusters :505-552, cluster :564-629) but every O(N) step is a kernel
+// launch from kernels.cu on this engine's stream; the host keeps only the
+// K-sized posteriors (host_model.hpp) and the control decisions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "host_model.hpp"
+
+namespace lcb {
+
+typedef int (*HostAllreduceFn)(double* buf, int64_t count, void* ctx);
+
+// A set of rows resident on the device together with two responsibility
+// buffers (current + candidate).
+struct View {
+  int64_t N = 0;  // local rows
+  int D = 0;
+  int64_t ldx = 0;
+  int J = 1;
+  void* X = nullptr;
+  int32_t* gid = nullptr;
+  void* q = nullptr;
+  void* q2 = nullptr;
+  int64_t ldq = 0;
+  int K = 0;
+  bool owns_x = false;
+};
+
+struct DeviceBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+class Engine {
+ public:
+  Engine(int device, int precision);
+  ~Engine();
+
+  void set_data_host(int J, const double* const* X, const int64_t* Nj, int D, const int64_t* ld, int layout);
+  void set_data_device_f32(const float* X, int64_t N, int D, int64_t ld, const int32_t* gid, int J);
+
+  void learn(int model, double prior, double wprior, int maxclusters, bool sparse, bool verbose, unsigned nthreads,
+             double* F, int* K);
+  void model_init(int model, double prior, double wprior, bool sparse);
+  void set_qz(const double* q0, int K);
+  void set_labels_device(const int32_t* labels, int K);
+  void vbem_public(int maxit, double* F, int* iters);
+  void vbem_step(double* F);
+
+  int num_clusters() const { return (int)clusters_.size(); }
+  int num_groups() const { return main_.J; }
+  int64_t num_rows(int j) const;
+  void get_qz(int j, double* out, int64_t ld, int layout);
+  void get_group_weights(int j, double* Nk, double* Elogw, double* fen);
+  void get_cluster(int k, double* N_s, double* x_s, double* xx_s, double* N, double* mean, double* cov, double* fen);
+  const std::vector<double>& trace_F() const { return trace_F_; }
+  const std::vector<int>& trace_K() const { return trace_K_; }
+  void get_step_timing(double out[4]);
+  cudaStream_t stream() const { return stream_; }
+
+  void comm_init_nccl(const char id[128], int rank, int world);
+  void comm_init_host(HostAllreduceFn fn, void* ctx, int rank, int world);
+
+  // operator-level ops on host buffers (distributions.h surface)
+  void op_addobs(ClusterPost& c, const double* qk, const double* X, int64_t N, int64_t ld, int layout);
+  void op_eloglike(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, double* out);
+  void op_splitobs(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, uint8_t* out);
+
+ private:
+  template <typename T> void upload_rows(View& v, const double* const* X, const int64_t* Nj, const int64_t* ld, int J,
+                                         int layout, const std::vector<double>& mean);
+  void free_view(View& v);
+  void ensure_q(View& v, int K);
+  void swap_q(View& v) { std::swap(v.q, v.q2); }
+  void reserve(DeviceBuf& b, size_t bytes);
+  void* pinned(size_t bytes);
+
+  // one vbem() on a view; clusters/weights are resized like the reference does
+  double vbem(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+              std::vector<std::vector<double>>& hints, int maxit, bool record, int* iters);
+  void iteration(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                 std::vector<std::vector<double>>& hints, double* F);
+  void sphase(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+              const std::vector<std::vector<double>>& centres);
+  double ephase(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters, int mode,
+                std::vector<double>* H);
+  void group_counts(View& v, std::vector<double>& Njk);
+  bool prune(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters);
+  bool split_gr(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                std::vector<int>& tally, double F, int maxclusters);
+  void build_act(const std::vector<double>& Njk, int J, int K);
+  void allreduce(double* dev, int64_t count);
+  void allreduce_host(double* host, int64_t count);
+  void check(cudaError_t e, const char* what) const;
+  void sync();
+
+  int device_, prec_, sms_;
+  cudaStream_t stream_ = nullptr;
+  View main_;
+  std::vector<int64_t> Nj_;       // local rows per group
+  std::vector<double> centre_;    // global column mean subtracted at upload
+  int64_t N_total_ = 0;           // rows over all ranks
+
+  // model state of the current fit
+  int model_ = -1, wkind_ = 0, ckind_ = 0;
+  double prior_ = 1.0, wprior_ = -1.0;
+  bool sparse_ = false, verbose_ = false;
+  std::vector<WeightPost> weights_;
+  std::vector<ClusterPost> clusters_;
+  std::vector<std::vector<double>> hints_;
+  std::vector<double> trace_F_;
+  std::vector<int> trace_K_;
+  double last_F_ = 0;
+  int64_t v_ntot_ = 0;        // rows (all ranks) of the view the current vbem runs on
+  bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
+
+  // device scratch
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_;
+  std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
+  void* h_pin_ = nullptr;
+  size_t h_pin_bytes_ = 0;
+
+  // timing of the last step
+  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  double t_s_ = 0, t_e_ = 0, t_all_ = 0;
+  long launches_ = 0, step_launches_ = 0;
+
+  // communication
+  int rank_ = 0, world_ = 1;
+  void* nccl_comm_ = nullptr;
+  HostAllreduceFn host_ar_ = nullptr;
+  void* host_ar_ctx_ = nullptr;
+};
+
+// NCCL resolved at run time (dlopen) so that the library loads without it.
+int nccl_get_unique_id(char out[128], std::string* err);
+
+}  // namespace lcb
