@@ -315,11 +315,18 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
     for (int j = 0; j < J && left > 0; ++j) {
       const int64_t ldj = ld ? ld[j] : (layout == 0 ? D : Nj[j]);
       const int64_t take = std::min(left, Nj[j]);
-      for (int d = 0; d < D; ++d) {
-        double s = 0;
-        if (layout == 0) for (int64_t n = 0; n < take; ++n) s += X[j][n * ldj + d];
-        else for (int64_t n = 0; n < take; ++n) s += X[j][(int64_t)d * ldj + n];
-        sums[d] += s;
+      if (layout == 0) {
+        for (int64_t n = 0; n < take; ++n) {
+          const double* row = X[j] + n * ldj;
+          for (int d = 0; d < D; ++d) sums[d] += row[d];
+        }
+      } else {
+        for (int d = 0; d < D; ++d) {
+          double s = 0;
+          const double* col = X[j] + (int64_t)d * ldj;
+          for (int64_t n = 0; n < take; ++n) s += col[n];
+          sums[d] += s;
+        }
       }
       sums[D] += (double)take;
       left -= take;
