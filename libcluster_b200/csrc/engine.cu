@@ -6,10 +6,12 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 
 #include "kernels.cuh"
+#include "tc_kernels.cuh"
 
 namespace lcb {
 
@@ -90,13 +92,15 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   sms_ = prop.multiProcessorCount;
   check(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate");
   for (auto& e : ev_) check(cudaEventCreate(&e), "cudaEventCreate");
+  const char* no_tc = std::getenv("LCB_DISABLE_TC");
+  use_tc_ = !(no_tc && no_tc[0] && no_tc[0] != '0');
 }
 
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
@@ -535,6 +539,8 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
                       int mode, std::vector<double>* H) {
   const int J = v.J, K = v.K, D = v.D;
   const bool full = ckind_ == kGaussWish;
+  if (mode == dev::kEWrite && prec_ == kF32 && full && use_tc_ && dev::tc_supported(D, v.ldx) && v.N > 0)
+    return ephase_tc(v, weights, clusters);
   const size_t es = prec_ == kF32 ? 4 : 8;
   const int DP = full ? dev::full_dp(D) : D;
   if (full && DP == 0) throw_invalid("full-covariance models support D <= 256");
@@ -627,6 +633,89 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
     H->assign(out.begin() + 1, out.end());
     H->push_back(cbar);  // caller adds cbar * Nk
   }
+  return -(out[0] + (double)v_ntot_ * cbar);
+}
+
+// E step on the tensor cores (D == 128, fp32 engine): operands are packed on the
+// host as pre-swizzled fp16 hi/lo blobs with per-cluster power-of-two scales.
+double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters) {
+  const int J = v.J, K = v.K, D = v.D;
+  const size_t nblob = (size_t)K * dev::kTcBlobBytes;
+  const size_t nfl = (size_t)2 * K * D + 3 * (size_t)K + (size_t)J * K;  // mhi, mlo, ascale, inv_t2, chat, lw
+  const size_t total = nblob + nfl * sizeof(float) + 16;
+  unsigned char* h = (unsigned char*)pinned(total);
+  float* f = reinterpret_cast<float*>(h + nblob);
+  float* h_mhi = f;
+  float* h_mlo = h_mhi + (size_t)K * D;
+  float* h_as = h_mlo + (size_t)K * D;
+  float* h_it2 = h_as + K;
+  float* h_chat = h_it2 + K;
+  float* h_lw = h_chat + K;
+  std::vector<double> cc(K);
+  double cbar = 0;
+  for (int k = 0; k < K; ++k) {
+    cc[k] = clusters[k].cconst();
+    cbar += cc[k];
+  }
+  cbar /= K;
+#pragma omp parallel for schedule(dynamic)
+  for (int k = 0; k < K; ++k) {
+    std::vector<double> R;
+    clusters[k].whitener(R);
+    // a = s (x - m): s maps the widest posterior standard deviation to ~32
+    const std::vector<double> cov = clusters[k].cov();
+    double vmax = 0, rmax = 0;
+    for (int d = 0; d < D; ++d) vmax = std::max(vmax, cov[(size_t)d * D + d]);
+    for (size_t i = 0; i < R.size(); ++i) rmax = std::max(rmax, std::fabs(R[i]));
+    int es_ = (int)std::lround(std::log2(32.0 / std::sqrt(std::max(vmax, 1e-300))));
+    es_ = std::min(60, std::max(-60, es_));
+    const double s = std::ldexp(1.0, es_);
+    // b = (t / s) R: t puts the largest entry of R / s near 2^8
+    int et = 8 - (int)std::ceil(std::log2(std::max(rmax / s, 1e-300)));
+    et = std::min(100, std::max(-100, et));
+    const double t = std::ldexp(1.0, et);
+    dev::tc_pack_cluster(R.data(), t / s, h + (size_t)k * dev::kTcBlobBytes);
+    h_as[k] = (float)s;
+    h_it2[k] = (float)(1.0 / (t * t));
+    const std::vector<double>& m = clusters[k].mean();
+    for (int d = 0; d < D; ++d) {
+      const double rel = m[d] - centre_[d];
+      const float hi = (float)rel;
+      h_mhi[(size_t)k * D + d] = hi;
+      h_mlo[(size_t)k * D + d] = (float)(rel - (double)hi);
+    }
+    h_chat[k] = (float)(cc[k] - cbar);
+  }
+  for (int j = 0; j < J; ++j) {
+    const std::vector<double>& e = weights[j].Elogweight();
+    for (int k = 0; k < K; ++k) h_lw[(size_t)j * K + k] = (float)e[k];
+  }
+  reserve(d_tc_, total);
+  check(cudaMemcpyAsync(d_tc_.p, h, total, cudaMemcpyHostToDevice, stream_), "H2D tc params");
+  const uint8_t* d_blob = (const uint8_t*)d_tc_.p;
+  const float* df = reinterpret_cast<const float*>(d_blob + nblob);
+  const float* d_mhi = df;
+  const float* d_mlo = d_mhi + (size_t)K * D;
+  const float* d_as = d_mlo + (size_t)K * D;
+  const float* d_it2 = d_as + K;
+  const float* d_chat = d_it2 + K;
+  const float* d_lw = d_chat + K;
+  const uint8_t* d_act = (sparse_ && !act_.empty()) ? (const uint8_t*)d_act_.p : nullptr;
+
+  reserve(d_small_, sizeof(double) * (K + 4));
+  double* d_fz = (double*)d_small_.p;
+  unsigned* d_err = (unsigned*)(d_fz + 1);
+  check(cudaMemsetAsync(d_fz, 0, sizeof(double) * 2, stream_), "memset");
+  check(cudaEventRecord(ev_[2], stream_), "event");
+  check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_mhi, d_mlo, d_as, d_it2, d_chat, d_lw,
+                         d_act, (float*)v.q, v.ldq, d_fz, d_err),
+        "estep_tc128 launch");
+  ++launches_;
+  check(cudaEventRecord(ev_[3], stream_), "event");
+  allreduce(d_fz, 1);
+  double out[2] = {0, 0};
+  check(cudaMemcpyAsync(out, d_fz, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream_), "D2H Fz");
+  sync();
   return -(out[0] + (double)v_ntot_ * cbar);
 }
 

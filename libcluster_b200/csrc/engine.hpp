@@ -91,6 +91,7 @@ class Engine {
               const std::vector<std::vector<double>>& centres);
   double ephase(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters, int mode,
                 std::vector<double>* H);
+  double ephase_tc(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters);
   void group_counts(View& v, std::vector<double>& Njk);
   bool prune(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters);
   bool split_gr(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
@@ -102,6 +103,7 @@ class Engine {
   void sync();
 
   int device_, prec_, sms_;
+  bool use_tc_ = true;  // tcgen05 tier of the E step (LCB_DISABLE_TC=1 forces the SIMT tier)
   cudaStream_t stream_ = nullptr;
   View main_;
   std::vector<int64_t> Nj_;       // local rows per group
@@ -122,7 +124,7 @@ class Engine {
   bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
 
   // device scratch
-  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_;
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_;
   std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;

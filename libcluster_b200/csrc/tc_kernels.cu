@@ -1,0 +1,388 @@
+// tc_kernels.cu -- tcgen05 (5th-gen tensor core) tier of the E step, sm_100a only.
+//
+// estep_tc128_kernel: full-covariance E step for D == 128 in the fp32 engine.
+//   logit[n,k] = chat_k + lw[g,k] - 0.5 * | R_k (x_n - m_k) |^2
+// The whitening Y_k = (X - m_k) R_k^T of one 128-point tile is a 128x128x128
+// GEMM per cluster.  It runs on the tensor cores at fp32-equivalent accuracy
+// by splitting both operands into fp16 (hi, lo) pairs and issuing the three
+// significant products  hi*hi + hi*lo + lo*hi  into one fp32 TMEM accumulator:
+//   A_k = s_k (X - m_k)   centred per cluster in fp32 *before* the split (the
+//                         cancellation must not happen inside the accumulator)
+//   B_k = (t_k / s_k) R_k lower-triangular; packed by the host as pre-swizzled
+//                         fp16 hi/lo blobs (engine.cu: pack_tc_operands)
+// with s_k, t_k powers of two chosen so that both stay in fp16's normal range.
+// Because R_k is lower-triangular the K-chunk covering input dims [16c,16c+16)
+// only feeds output columns i >= 16c: the MMA for that chunk runs with
+// N = 128 - 16c (56 % of the dense work).
+//
+// One persistent CTA per SM, 16 warps:
+//   warp 0      producer: cp.async.bulk (TMA engine) of the X tile and of the
+//               per-cluster operand blobs into a 2-stage ring
+//   warp 1      one lane issues tcgen05.mma, commits to mbarriers
+//   warp 2      TMEM allocation (2 accumulators x 128 columns)
+//   warps 4-7   epilogue: tcgen05.ld accumulator -> sum of squares -> logit;
+//               after the last cluster: row soft-max, q and log Z
+//   warps 8-15  operand builders: centre, scale, split, swizzled st.shared of
+//               A (4 warps per 64-dim K block so the blocks pipeline with MMA)
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.cuh"
+#include "tc_kernels.cuh"
+
+namespace lcb {
+namespace dev {
+
+namespace {
+
+constexpr int kD = 128;
+constexpr int kTM = 128;
+constexpr uint32_t kXBytes = kTM * kD * 4;        // 65536
+constexpr uint32_t kAPart = kTM * 128;            // one fp16 [128 x 64] swizzled block: 16384
+constexpr uint32_t kABytes = 4 * kAPart;          // kb0 hi, kb0 lo, kb1 hi, kb1 lo
+constexpr uint32_t kBBlob = kTcBlobBytes;         // 49152: kb0 hi(16K) lo(16K) kb1 hi(8K) lo(8K)
+constexpr uint32_t kOffX = 0;
+constexpr uint32_t kOffA = kOffX + kXBytes;
+constexpr uint32_t kOffB = kOffA + kABytes;
+constexpr uint32_t kOffBar = kOffB + 2 * kBBlob;  // 229376
+constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
+constexpr int kThreadsTc = 512;
+constexpr uint32_t kTmemCols = 256;
+
+// barrier slots (8 bytes each) after kOffBar
+enum { BX_FULL = 0, BX_EMPTY, BA_FULL0, BA_FULL1, BA_EMPTY0, BA_EMPTY1, BB_FULL0, BB_FULL1, BB_EMPTY0, BB_EMPTY1,
+       BT_FULL0, BT_FULL1, BT_EMPTY0, BT_EMPTY1, B_COUNT };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a protocol bug becomes a trap (reported by the host) instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned* err) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > (1u << 22)) {
+      if (err) atomicExch(err, 0xdead0000u | (bar & 0xffffu));
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFFu);       // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024u >> 4) << 32;             // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=f16, both K-major, M=128, N=n
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __restrict__ gid, int K,
+                   const uint8_t* __restrict__ blob, const float* __restrict__ mhi, const float* __restrict__ mlo,
+                   const float* __restrict__ ascale, const float* __restrict__ inv_t2, const float* __restrict__ chat,
+                   const float* __restrict__ lw, const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq,
+                   double* __restrict__ Fz, unsigned* __restrict__ err) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
+  const uint32_t sX = sbase + kOffX, sA = sbase + kOffA, sB = sbase + kOffB, sBar = sbase + kOffBar;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * B_COUNT);
+  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (N + kTM - 1) / kTM;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(BX_FULL), 1);
+    mbar_init(bar(BX_EMPTY), 8);
+    mbar_init(bar(BA_FULL0), 4);
+    mbar_init(bar(BA_FULL1), 4);
+    mbar_init(bar(BA_EMPTY0), 1);
+    mbar_init(bar(BA_EMPTY1), 1);
+    mbar_init(bar(BB_FULL0), 1);
+    mbar_init(bar(BB_FULL1), 1);
+    mbar_init(bar(BB_EMPTY0), 1);
+    mbar_init(bar(BB_EMPTY1), 1);
+    mbar_init(bar(BT_FULL0), 1);
+    mbar_init(bar(BT_FULL1), 1);
+    mbar_init(bar(BT_EMPTY0), 4);
+    mbar_init(bar(BT_EMPTY1), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"(kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ producer --
+    if (lane == 0) {
+      uint32_t it = 0, bcount = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int64_t n0 = tile * kTM;
+        const uint32_t rows = (uint32_t)((N - n0 < kTM) ? (N - n0) : kTM);
+        mbar_wait(bar(BX_EMPTY), (it & 1) ^ 1, err);
+        mbar_expect_tx(bar(BX_FULL), rows * kD * 4);
+        bulk_g2s(sX, X + n0 * kD, rows * kD * 4, bar(BX_FULL));
+        for (int k = 0; k < K; ++k, ++bcount) {
+          const uint32_t st = bcount & 1, ph = (bcount >> 1) & 1;
+          mbar_wait(bar(BB_EMPTY0 + st), ph ^ 1, err);
+          mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
+          bulk_g2s(sB + st * kBBlob, blob + (size_t)k * kBBlob, kBBlob, bar(BB_FULL0 + st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ---------------------------------------------------------- MMA issuer --
+    if (lane == 0) {
+      uint32_t cnt = 0;  // clusters processed so far (all rings advance once per cluster)
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int k = 0; k < K; ++k, ++cnt) {
+          const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
+          mbar_wait(bar(BT_EMPTY0 + st), ph ^ 1, err);
+          mbar_wait(bar(BB_FULL0 + st), ph, err);
+          const uint32_t sBk = sB + st * kBBlob;
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb) {
+            mbar_wait(bar(BA_FULL0 + kb), cnt & 1, err);
+            tc_fence_after();
+            const uint32_t a_hi = sA + (uint32_t)kb * 2 * kAPart, a_lo = a_hi + kAPart;
+            const uint32_t b_hi = sBk + (kb == 0 ? 0u : 2 * kAPart);
+            const uint32_t b_lo = b_hi + (kb == 0 ? kAPart : kAPart / 2);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const uint32_t c = 4 * kb + c4, nc = 128 - 16 * c;
+              const uint32_t rowoff = (16 * c - 64 * kb) * 128;  // first needed row inside the stored block
+              const uint32_t koff = 32 * c4;                      // 16 fp16 along K inside the 128-byte row
+              const uint32_t d = tmem_base + st * 128 + 16 * c;
+              const uint32_t id = umma_idesc(nc);
+              const uint64_t dah = umma_desc(a_hi + koff), dal = umma_desc(a_lo + koff);
+              const uint64_t dbh = umma_desc(b_hi + rowoff + koff), dbl = umma_desc(b_lo + rowoff + koff);
+              tc_mma_f16(d, dah, dbh, id, (kb | c4) ? 1u : 0u);
+              tc_mma_f16(d, dah, dbl, id, 1u);
+              tc_mma_f16(d, dal, dbh, id, 1u);
+            }
+            tc_commit(bar(BA_EMPTY0 + kb));
+          }
+          tc_commit(bar(BB_EMPTY0 + st));
+          tc_commit(bar(BT_FULL0 + st));
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------- epilogue --
+    const int ew = warp - 4;
+    double fz = 0;
+    uint32_t cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t n = tile * kTM + ew * 32 + lane;
+      const bool valid = n < N;
+      const int g = (gid != nullptr && valid) ? gid[n] : 0;
+      const float* lwg = lw + (size_t)g * K;
+      const uint8_t* actg = act != nullptr ? act + (size_t)g * K : nullptr;
+      float* qrow = q + (valid ? n : 0) * ldq;
+      float mx = -INFINITY, se = 0.f;  // running max / sum of exp for the row soft-max
+      for (int k = 0; k < K; ++k, ++cnt) {
+        const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
+        mbar_wait(bar(BT_FULL0 + st), ph, err);
+        tc_fence_after();
+        float s = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + st * 128 + 32 * cc, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s = fmaf(v[i], v[i], s);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BT_EMPTY0 + st));
+        float l = chat[k] + lwg[k] - 0.5f * inv_t2[k] * s;
+        if (actg != nullptr && !actg[k]) l = -INFINITY;
+        if (valid) qrow[k] = l;
+        if (l > mx) {
+          se = se * expf(mx - l) + 1.f;
+          mx = l;
+        } else if (l > -INFINITY) {
+          se += expf(l - mx);
+        }
+      }
+      if (valid) {
+        // q = exp(logit - logZ) from the logits parked in the q row (L2-resident)
+        const float lz = logf(se) + mx;
+        float4* q4 = reinterpret_cast<float4*>(qrow);
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+          float4 v = q4[k >> 2];
+          v.x = expf(v.x - lz); v.y = expf(v.y - lz); v.z = expf(v.z - lz); v.w = expf(v.w - lz);
+          q4[k >> 2] = v;
+        }
+        for (; k < K; ++k) qrow[k] = expf(qrow[k] - lz);
+        fz += (double)lz;
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
+    if (lane == 0) atomicAdd(Fz, fz);
+  } else if (warp >= 8) {
+    // ------------------------------------------------------ operand builders --
+    const int bw = warp - 8, kb = bw >> 2, sub = bw & 3;
+    const int d = 64 * kb + 2 * lane;
+    const float* xs = reinterpret_cast<const float*>(sgen + kOffX);
+    const uint32_t a_hi = sA + (uint32_t)kb * 2 * kAPart, a_lo = a_hi + kAPart;
+    uint32_t it = 0, cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      mbar_wait(bar(BX_FULL), it & 1, err);
+      for (int k = 0; k < K; ++k, ++cnt) {
+        const float2 mh = *reinterpret_cast<const float2*>(mhi + (size_t)k * kD + d);
+        const float2 ml = *reinterpret_cast<const float2*>(mlo + (size_t)k * kD + d);
+        const float sc = ascale[k];
+        mbar_wait(bar(BA_EMPTY0 + kb), (cnt & 1) ^ 1, err);
+#pragma unroll 8
+        for (int r = 0; r < 32; ++r) {
+          const int nrow = sub * 32 + r;
+          const float2 x = *reinterpret_cast<const float2*>(xs + nrow * kD + d);
+          const float a0 = ((x.x - mh.x) - ml.x) * sc;
+          const float a1 = ((x.y - mh.y) - ml.y) * sc;
+          const uint32_t hi = pack_f16x2_sat(a0, a1);
+          const __half2 hh = *reinterpret_cast<const __half2*>(&hi);
+          const float2 hf = __half22float2(hh);
+          const uint32_t lo = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
+          const uint32_t off = (uint32_t)nrow * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)nrow & 7u)) << 4) +
+                               (((uint32_t)lane & 3u) << 2);
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_hi + off), "r"(hi) : "memory");
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_lo + off), "r"(lo) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BA_FULL0 + kb));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BX_EMPTY));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+}  // namespace
+
+bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
+
+cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
+                        const uint8_t* blob, const float* mhi, const float* mlo, const float* ascale,
+                        const float* inv_t2, const float* chat, const float* lw, const uint8_t* act, float* q,
+                        int64_t ldq, double* Fz, unsigned* err) {
+  if (N <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return e;
+  const int64_t ntiles = (N + kTM - 1) / kTM;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  estep_tc128_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, mhi, mlo, ascale, inv_t2, chat, lw, act,
+                                                           q, ldq, Fz, err);
+  return cudaGetLastError();
+}
+
+// Host-side packing of one cluster's B operand: Bs[i][d] = R[i][d] * bscale,
+// i >= d, split into fp16 hi/lo and laid out exactly as the kernel's shared
+// memory expects (row pitch 128 B = 64 fp16 of one K block, 16-byte chunks
+// XOR-swizzled with row % 8; K block 1 stores rows 64..127 only).
+void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */, double bscale, uint8_t* out) {
+  for (uint32_t i = 0; i < kBBlob; ++i) out[i] = 0;
+  for (int kbk = 0; kbk < 2; ++kbk) {
+    const uint32_t base_hi = kbk == 0 ? 0u : 2 * kAPart;
+    const uint32_t base_lo = base_hi + (kbk == 0 ? kAPart : kAPart / 2);
+    for (int i = 64 * kbk; i < 128; ++i) {
+      const int r = i - 64 * kbk;
+      for (int kk = 0; kk < 64; ++kk) {
+        const int dcol = 64 * kbk + kk;
+        if (dcol > i) continue;
+        const float v = (float)(R[(size_t)i * 128 + dcol] * bscale);
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        const uint32_t off = (uint32_t)r * 128u + ((((uint32_t)kk >> 3) ^ ((uint32_t)r & 7u)) << 4) + (((uint32_t)kk & 7u) << 1);
+        *reinterpret_cast<__half*>(out + base_hi + off) = h;
+        *reinterpret_cast<__half*>(out + base_lo + off) = l;
+      }
+    }
+  }
+}
+
+}  // namespace dev
+}  // namespace lcb

@@ -1,0 +1,94 @@
+"""GPU (-m gpu): the tcgen05 tier of the E step (D = 128, fp32 engine) against the
+oracle and against the SIMT tier of the same engine (LCB_DISABLE_TC=1)."""
+import os
+
+import numpy as np
+import pytest
+
+import libcluster_b200 as lc
+from conftest import make_blobs, soft_labels
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(tc):
+    if tc:
+        os.environ.pop("LCB_DISABLE_TC", None)
+    else:
+        os.environ["LCB_DISABLE_TC"] = "1"
+    try:
+        return lc.Engine(0, lc.F32)
+    finally:
+        os.environ.pop("LCB_DISABLE_TC", None)
+
+
+@pytest.mark.parametrize("N,K,spread", [(100, 1, 3.0), (128, 2, 3.0), (1000, 3, 2.0), (5000, 7, 4.0), (4097, 16, 1.5),
+                                        (20000, 33, 3.0)])
+def test_tc_estep_matches_oracle_and_simt(N, K, spread):
+    D = 128
+    X, z = make_blobs(N, D, K, seed=N + K, spread=spread)
+    q0 = soft_labels(z, K, seed=K)
+    m = po.Model(po.BGMM, [X])
+    m.vbem(q0, maxit=2)
+    Fo, _ = m.trace()
+    res = {}
+    for tc in (True, False):
+        eng = _engine(tc)
+        eng.set_data(X)
+        eng.model_init(lc.BGMM)
+        eng.set_qz(q0)
+        eng.vbem(maxit=2)
+        res[tc] = (eng.trace()[0], eng.qZ(0))
+        eng.close()
+    for tc in (True, False):
+        Fe, q = res[tc]
+        assert len(Fe) == len(Fo)
+        assert np.allclose(Fe, Fo, rtol=1e-5), (tc, Fe, Fo)
+        assert np.abs(q - m.qZ()).max() <= 1e-5, tc
+        assert np.allclose(q.sum(1), 1.0, atol=1e-5)
+    assert np.allclose(res[True][0], res[False][0], rtol=2e-6)
+    assert np.abs(res[True][1] - res[False][1]).max() <= 5e-6
+
+
+def test_tc_overlapping_clusters_keep_1e5():
+    """Two heavily overlapping clusters far from the origin: the per-cluster centring before the fp16
+    split is what keeps qZ within 1e-5 here."""
+    rng = np.random.default_rng(0)
+    D, N = 128, 6000
+    base = rng.uniform(-20, 20, size=D)
+    X = np.concatenate([base + rng.normal(size=(N // 2, D)), base + 0.15 + 1.05 * rng.normal(size=(N // 2, D))])
+    z = np.repeat([0, 1], N // 2)
+    q0 = soft_labels(z, 2, seed=1, noise=0.6)
+    m = po.Model(po.VDP, [X])
+    m.vbem(q0, maxit=3)
+    eng = _engine(True)
+    eng.set_data(X)
+    eng.model_init(lc.VDP)
+    eng.set_qz(q0)
+    eng.vbem(maxit=3)
+    q = eng.qZ(0)
+    qo = m.qZ()
+    assert ((qo > 0.05) & (qo < 0.95)).mean() > 0.1          # genuinely soft assignments
+    assert np.abs(q - qo).max() <= 1e-5
+    assert np.allclose(eng.trace()[0], m.trace()[0], rtol=1e-5)
+    eng.close()
+
+
+def test_tc_grouped_sparse_and_full_learn():
+    D = 128
+    X, z = make_blobs(2400, D, 3, seed=3, spread=5.0)
+    order = np.argsort(z, kind="stable")
+    X = X[order]
+    groups = [X[:900], X[900:1000], X[1000:]]
+    for sparse in (False, True):
+        m = po.Model(po.GMC, groups)
+        m.learn(sparse=sparse)
+        eng = _engine(True)
+        eng.set_data(groups)
+        eng.learn(lc.GMC, sparse=sparse)
+        assert eng.K == m.K
+        q = np.concatenate(eng.qZ(), 0)
+        assert np.abs(q - m.qZ()).max() <= 1e-5
+        assert eng.trace()[0][-1] == pytest.approx(m.trace()[0][-1], rel=1e-5)
+        eng.close()
