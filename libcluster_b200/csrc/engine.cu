@@ -100,7 +100,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
@@ -492,41 +492,78 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
   else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
   ++launches_;
-  std::vector<double> host((size_t)nstat);
+  std::vector<double> host_njk;  // sparse mode reads the counts early
   const uint8_t* d_act = nullptr;
   if (sparse_) {
     allreduce(d_njk, nJK);
-    check(cudaMemcpyAsync(host.data(), d_njk, sizeof(double) * nJK, cudaMemcpyDeviceToHost, stream_), "D2H Njk");
+    host_njk.resize((size_t)nJK);
+    check(cudaMemcpyAsync(host_njk.data(), d_njk, sizeof(double) * nJK, cudaMemcpyDeviceToHost, stream_), "D2H Njk");
     sync();
-    build_act(host, J, K);
+    build_act(host_njk, J, K);
     d_act = (const uint8_t*)d_act_.p;
   }
-  cudaError_t ke;
-  if (prec_ == kF32) {
-    ke = full ? dev::sstat_full<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
-                                        (const float*)d_cen_.p, d_act, d_xs, d_S)
-              : dev::sstat_diag<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
-                                        (const float*)d_cen_.p, d_act, d_xs, d_S);
+  cudaError_t ke = cudaSuccess;
+  if (full) {
+    // statistics over the non-zero responsibilities only: per-cluster (row, q) lists, then a gathered scatter
+    if (v.N > 0) {
+      const int64_t nb = dev::nz_blocks(v.N);
+      reserve(d_nzcnt_, sizeof(int32_t) * (size_t)nb * K);
+      reserve(d_nzoff_, sizeof(long long) * (size_t)(2 * K + 2));
+      int32_t* d_cnt = (int32_t*)d_nzcnt_.p;
+      long long* d_tot = (long long*)d_nzoff_.p;
+      long long* d_koff = d_tot + K;
+      if (prec_ == kF32) check(dev::nz_count<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt), "nz_count");
+      else check(dev::nz_count<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt), "nz_count");
+      check(dev::nz_scan(stream_, d_cnt, nb, K, d_tot), "nz_scan");
+      std::vector<long long> tot(K), koff(K);
+      check(cudaMemcpyAsync(tot.data(), d_tot, sizeof(long long) * K, cudaMemcpyDeviceToHost, stream_), "D2H nz totals");
+      sync();
+      long long nnz = 0, maxcnt = 0;
+      for (int k = 0; k < K; ++k) {
+        koff[k] = nnz;
+        nnz += tot[k];
+        maxcnt = std::max(maxcnt, tot[k]);
+      }
+      launches_ += 2;
+      if (nnz > 0) {
+        check(cudaMemcpyAsync(d_koff, koff.data(), sizeof(long long) * K, cudaMemcpyHostToDevice, stream_), "H2D koff");
+        const size_t rows_bytes = (size_t)round_up((int64_t)nnz * 4, 256);
+        reserve(d_list_, rows_bytes + (size_t)nnz * es + 256);
+        int32_t* lrow = (int32_t*)d_list_.p;
+        void* lq = (unsigned char*)d_list_.p + rows_bytes;
+        if (prec_ == kF32) {
+          check(dev::nz_fill<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (float*)lq), "nz_fill");
+          ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
+                                             maxcnt, K, (const float*)d_cen_.p, d_xs, d_S);
+        } else {
+          check(dev::nz_fill<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (double*)lq), "nz_fill");
+          ke = dev::sstat_gather_full<double>(stream_, (const double*)v.X, D, v.ldx, lrow, (const double*)lq, d_koff,
+                                              d_tot, maxcnt, K, (const double*)d_cen_.p, d_xs, d_S);
+        }
+        ++launches_;
+      }
+    }
+  } else if (prec_ == kF32) {
+    ke = dev::sstat_diag<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
+                                (const float*)d_cen_.p, d_act, d_xs, d_S);
   } else {
-    ke = full ? dev::sstat_full<double>(stream_, (const double*)v.X, v.N, D, v.ldx, v.gid, (const double*)v.q, v.ldq, K,
-                                         (const double*)d_cen_.p, d_act, d_xs, d_S)
-              : dev::sstat_diag<double>(stream_, (const double*)v.X, v.N, D, v.ldx, v.gid, (const double*)v.q, v.ldq,
-                                         K, (const double*)d_cen_.p, d_act, d_xs, d_S);
+    ke = dev::sstat_diag<double>(stream_, (const double*)v.X, v.N, D, v.ldx, v.gid, (const double*)v.q, v.ldq, K,
+                                 (const double*)d_cen_.p, d_act, d_xs, d_S);
   }
   check(ke, "sstat kernel");
   ++launches_;
   check(cudaEventRecord(ev_[1], stream_), "event");
   if (sparse_) allreduce(d_xs, nstat - nJK);
   else allreduce(d_njk, nstat);
-  check(cudaMemcpyAsync(host.data() + (sparse_ ? nJK : 0), sparse_ ? d_xs : d_njk,
-                        sizeof(double) * (sparse_ ? nstat - nJK : nstat), cudaMemcpyDeviceToHost, stream_),
-        "D2H stats");
+  double* host = (double*)pinned(sizeof(double) * (size_t)nstat);
+  check(cudaMemcpyAsync(host, d_njk, sizeof(double) * nstat, cudaMemcpyDeviceToHost, stream_), "D2H stats");
   sync();
 
-  const double* Njk = host.data();
+  const double* Njk = host;
   const double* xs = Njk + nJK;
   const double* S = xs + (int64_t)K * D;
   for (int j = 0; j < J; ++j) weights[j].update(Njk + (int64_t)j * K, K);
+#pragma omp parallel for schedule(dynamic) if (K >= 8)
   for (int k = 0; k < K; ++k) {
     double n = 0;
     for (int j = 0; j < J; ++j)
@@ -641,13 +678,11 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
 double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters) {
   const int J = v.J, K = v.K, D = v.D;
   const size_t nblob = (size_t)K * dev::kTcBlobBytes;
-  const size_t nfl = (size_t)2 * K * D + 3 * (size_t)K + (size_t)J * K;  // mhi, mlo, ascale, inv_t2, chat, lw
+  const size_t nfl = 3 * (size_t)K + (size_t)J * K;  // ascale, inv_t2, chat, lw
   const size_t total = nblob + nfl * sizeof(float) + 16;
   unsigned char* h = (unsigned char*)pinned(total);
   float* f = reinterpret_cast<float*>(h + nblob);
-  float* h_mhi = f;
-  float* h_mlo = h_mhi + (size_t)K * D;
-  float* h_as = h_mlo + (size_t)K * D;
+  float* h_as = f;
   float* h_it2 = h_as + K;
   float* h_chat = h_it2 + K;
   float* h_lw = h_chat + K;
@@ -658,7 +693,7 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     cbar += cc[k];
   }
   cbar /= K;
-#pragma omp parallel for schedule(dynamic)
+#pragma omp parallel for schedule(dynamic) if (K >= 8)
   for (int k = 0; k < K; ++k) {
     std::vector<double> R;
     clusters[k].whitener(R);
@@ -674,16 +709,12 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     int et = 8 - (int)std::ceil(std::log2(std::max(rmax / s, 1e-300)));
     et = std::min(100, std::max(-100, et));
     const double t = std::ldexp(1.0, et);
-    dev::tc_pack_cluster(R.data(), t / s, h + (size_t)k * dev::kTcBlobBytes);
+    const std::vector<double>& m = clusters[k].mean();
+    std::vector<double> rel(D);
+    for (int d = 0; d < D; ++d) rel[d] = m[d] - centre_[d];
+    dev::tc_pack_cluster(R.data(), t / s, rel.data(), s, h + (size_t)k * dev::kTcBlobBytes);
     h_as[k] = (float)s;
     h_it2[k] = (float)(1.0 / (t * t));
-    const std::vector<double>& m = clusters[k].mean();
-    for (int d = 0; d < D; ++d) {
-      const double rel = m[d] - centre_[d];
-      const float hi = (float)rel;
-      h_mhi[(size_t)k * D + d] = hi;
-      h_mlo[(size_t)k * D + d] = (float)(rel - (double)hi);
-    }
     h_chat[k] = (float)(cc[k] - cbar);
   }
   for (int j = 0; j < J; ++j) {
@@ -694,9 +725,7 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   check(cudaMemcpyAsync(d_tc_.p, h, total, cudaMemcpyHostToDevice, stream_), "H2D tc params");
   const uint8_t* d_blob = (const uint8_t*)d_tc_.p;
   const float* df = reinterpret_cast<const float*>(d_blob + nblob);
-  const float* d_mhi = df;
-  const float* d_mlo = d_mhi + (size_t)K * D;
-  const float* d_as = d_mlo + (size_t)K * D;
+  const float* d_as = df;
   const float* d_it2 = d_as + K;
   const float* d_chat = d_it2 + K;
   const float* d_lw = d_chat + K;
@@ -707,7 +736,7 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   unsigned* d_err = (unsigned*)(d_fz + 1);
   check(cudaMemsetAsync(d_fz, 0, sizeof(double) * 2, stream_), "memset");
   check(cudaEventRecord(ev_[2], stream_), "event");
-  check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_mhi, d_mlo, d_as, d_it2, d_chat, d_lw,
+  check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw,
                          d_act, (float*)v.q, v.ldq, d_fz, d_err),
         "estep_tc128 launch");
   ++launches_;
@@ -733,11 +762,31 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
   hints_first_ = false;
   for (int k = 0; k < K; ++k) clusters[k].clearobs();
   sphase(v, weights, clusters, centres);
-  for (int k = 0; k < K; ++k) clusters[k].update();
+  // VBM for the clusters (cluster.cpp:215-217 runs this loop under OpenMP as well)
+  {
+    int bad = 0;
+    Error first{0, ""};
+#pragma omp parallel for schedule(dynamic) if (K >= 8)
+    for (int k = 0; k < K; ++k) {
+      try {
+        clusters[k].update();
+      } catch (const Error& e) {
+#pragma omp critical
+        if (!bad) {
+          bad = 1;
+          first = e;
+        }
+      }
+    }
+    if (bad) throw first;
+  }
   const double Fz = ephase(v, weights, clusters, dev::kEWrite, nullptr);
   double Fw = 0, Fc = 0;
   for (size_t j = 0; j < weights.size(); ++j) Fw += weights[j].fenergy();
-  for (int k = 0; k < K; ++k) Fc += clusters[k].fenergy();
+  std::vector<double> fck(K);
+#pragma omp parallel for schedule(dynamic) if (K >= 8)
+  for (int k = 0; k < K; ++k) fck[k] = clusters[k].fenergy();
+  for (int k = 0; k < K; ++k) Fc += fck[k];
   *F = Fc + Fw + Fz;
 }
 

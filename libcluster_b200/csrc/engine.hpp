@@ -124,7 +124,7 @@ class Engine {
   bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
 
   // device scratch
-  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_;
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_;
   std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;

@@ -404,6 +404,209 @@ sstat_full_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
   if (bj == 0 && tid < BW && i0 + tid < D && xacc != (T)0) atomicAdd(&xs[(size_t)k * D + i0 + tid], (double)xacc);
 }
 
+
+// ---------------------------------------------------------------------------
+// Sufficient statistics over the NON-ZERO responsibilities only.
+//   nz_count : per (row block, cluster) number of rows with q != 0 (after the
+//              sparse-update mask)              -> blockcnt [nblocks][K]
+//   nz_scan  : per cluster exclusive scan over the row blocks (in place) and the
+//              per-cluster totals                -> total [K]
+//   nz_fill  : row index and q of every non-zero into per-cluster lists
+//   sstat_gather_full : per (cluster, 4096-row chunk of its list) the centred
+//              scatter on a register tile; fp32 partial sums are folded into an
+//              fp64 accumulator in shared memory every 64 rows so that the
+//              accumulation error stays ~1e-8 relative whatever N_k is.
+// ---------------------------------------------------------------------------
+constexpr int kNzBlock = 2048;  // rows per counting block
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+nz_count_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
+                const uint8_t* __restrict__ act, int32_t* __restrict__ blockcnt) {
+  extern __shared__ int scnt[];
+  for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * kNzBlock;
+  const int64_t r1 = (r0 + kNzBlock < N) ? r0 + kNzBlock : N;
+  const int64_t total = (r1 - r0) * K;
+  for (int64_t e = threadIdx.x; e < total; e += kThreads) {
+    const int64_t n = r0 + e / K;
+    const int k = (int)(e % K);
+    T v = q[n * ldq + k];
+    if (act != nullptr && v != (T)0) {
+      const int g = gid != nullptr ? gid[n] : 0;
+      if (!act[(size_t)g * K + k]) v = 0;
+    }
+    if (v != (T)0) atomicAdd(&scnt[k], 1);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += kThreads) blockcnt[(size_t)blockIdx.x * K + k] = scnt[k];
+}
+
+// one CTA per cluster: exclusive scan of its column of blockcnt
+__global__ void __launch_bounds__(kThreads)
+nz_scan_kernel(int32_t* __restrict__ blockcnt, int64_t nblocks, int K, long long* __restrict__ total) {
+  __shared__ long long part[kThreads];
+  const int k = blockIdx.x, t = threadIdx.x;
+  const int64_t per = (nblocks + kThreads - 1) / kThreads;
+  const int64_t b0 = (int64_t)t * per, b1 = (b0 + per < nblocks) ? b0 + per : nblocks;
+  long long s = 0;
+  for (int64_t b = b0; b < b1; ++b) s += blockcnt[(size_t)b * K + k];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    long long run = 0;
+    for (int i = 0; i < kThreads; ++i) {
+      const long long v = part[i];
+      part[i] = run;
+      run += v;
+    }
+    total[k] = run;
+  }
+  __syncthreads();
+  long long run = part[t];
+  for (int64_t b = b0; b < b1; ++b) {
+    const int v = blockcnt[(size_t)b * K + k];
+    blockcnt[(size_t)b * K + k] = (int32_t)run;
+    run += v;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+nz_fill_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
+               const uint8_t* __restrict__ act, const int32_t* __restrict__ blockoff,
+               const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq) {
+  extern __shared__ int scnt[];
+  for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * kNzBlock;
+  const int64_t r1 = (r0 + kNzBlock < N) ? r0 + kNzBlock : N;
+  const int64_t total = (r1 - r0) * K;
+  for (int64_t e = threadIdx.x; e < total; e += kThreads) {
+    const int64_t n = r0 + e / K;
+    const int k = (int)(e % K);
+    T v = q[n * ldq + k];
+    if (act != nullptr && v != (T)0) {
+      const int g = gid != nullptr ? gid[n] : 0;
+      if (!act[(size_t)g * K + k]) v = 0;
+    }
+    if (v != (T)0) {
+      const int pos = atomicAdd(&scnt[k], 1);
+      const long long o = koff[k] + blockoff[(size_t)blockIdx.x * K + k] + pos;
+      lrow[o] = (int32_t)n;
+      lq[o] = v;
+    }
+  }
+}
+
+constexpr int kGatherChunk = 4096;  // list rows per CTA
+
+template <typename T, int TN>
+__global__ void __launch_bounds__(kThreads)
+sstat_gather_full_kernel(const T* __restrict__ X, int D, int64_t ldx, const int32_t* __restrict__ lrow,
+                         const T* __restrict__ lq, const long long* __restrict__ koff,
+                         const long long* __restrict__ kcnt, int DPc, const T* __restrict__ cen, int nb,
+                         double* __restrict__ xs, double* __restrict__ S) {
+  constexpr int BW = 16 * TN, TMS = sizeof(T) == 8 ? 16 : 32;
+  constexpr bool kStage = sizeof(T) == 4;  // fp32: fold into fp64 shared accumulators every 2 sub-tiles
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* XI = reinterpret_cast<T*>(smem_raw);
+  T* XJ = XI + TMS * BW;
+  T* qs = XJ + TMS * BW;
+  int* rs = reinterpret_cast<int*>(qs + TMS);
+  double* Sacc = reinterpret_cast<double*>(smem_raw + (((size_t)(2 * TMS * BW + TMS) * sizeof(T) + TMS * 4 + 15) & ~(size_t)15));
+  double* xsacc = Sacc + (kStage ? TN * TN * kThreads : 0);
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int k = blockIdx.y;
+  const int bi = blockIdx.z / nb, bj = blockIdx.z - bi * nb;
+  const int i0 = bi * BW, j0 = bj * BW;
+  const long long cnt = kcnt[k];
+  const long long l0 = (long long)blockIdx.x * kGatherChunk;
+  if (l0 >= cnt) return;
+  const long long l1 = (l0 + kGatherChunk < cnt) ? l0 + kGatherChunk : cnt;
+  const long long base = koff[k];
+  const T* ck = cen + (size_t)k * DPc;
+
+  T acc[TN][TN];
+#pragma unroll
+  for (int a = 0; a < TN; ++a)
+#pragma unroll
+    for (int b = 0; b < TN; ++b) acc[a][b] = 0;
+  T xacc = 0;
+  if (kStage) {
+#pragma unroll
+    for (int e = 0; e < TN * TN; ++e) Sacc[e * kThreads + tid] = 0.0;
+    if (tid < BW) xsacc[tid] = 0.0;
+  }
+  int pending = 0;
+  for (long long t0 = l0; t0 < l1; t0 += TMS) {
+    __syncthreads();
+    if (tid < TMS) {
+      const long long l = t0 + tid;
+      qs[tid] = (l < l1) ? lq[base + l] : (T)0;
+      rs[tid] = (l < l1) ? lrow[base + l] : -1;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < TMS * BW; idx += kThreads) {
+      const int n = idx / BW, d = idx - n * BW;
+      const int r = rs[n];
+      T vi = 0, vj = 0;
+      if (r >= 0) {
+        if (i0 + d < D) vi = X[(int64_t)r * ldx + i0 + d] - ck[i0 + d];
+        if (j0 + d < D) vj = X[(int64_t)r * ldx + j0 + d] - ck[j0 + d];
+      }
+      XI[idx] = vi;
+      XJ[idx] = vj;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int n = 0; n < TMS; ++n) {
+      const T qn = qs[n];
+      T a[TN], b[TN];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) {
+        a[c] = XI[n * BW + ty + 16 * c];
+        b[c] = qn * XJ[n * BW + tx + 16 * c];
+      }
+#pragma unroll
+      for (int ci = 0; ci < TN; ++ci)
+#pragma unroll
+        for (int cj = 0; cj < TN; ++cj) acc[ci][cj] = fma(a[ci], b[cj], acc[ci][cj]);
+      if (bj == 0 && tid < BW) xacc = fma(qn, XI[n * BW + tid], xacc);
+    }
+    if (kStage && ++pending == 2) {
+      pending = 0;
+#pragma unroll
+      for (int ci = 0; ci < TN; ++ci)
+#pragma unroll
+        for (int cj = 0; cj < TN; ++cj) {
+          Sacc[(ci * TN + cj) * kThreads + tid] += (double)acc[ci][cj];
+          acc[ci][cj] = 0;
+        }
+      if (bj == 0 && tid < BW) {
+        xsacc[tid] += (double)xacc;
+        xacc = 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int ci = 0; ci < TN; ++ci)
+#pragma unroll
+    for (int cj = 0; cj < TN; ++cj) {
+      const int i = i0 + ty + 16 * ci, j = j0 + tx + 16 * cj;
+      double v = (double)acc[ci][cj];
+      if (kStage) v += Sacc[(ci * TN + cj) * kThreads + tid];
+      if (i < D && j < D && v != 0.0) atomicAdd(&S[((size_t)k * D + i) * D + j], v);
+    }
+  if (bj == 0 && tid < BW && i0 + tid < D) {
+    double v = (double)xacc;
+    if (kStage) v += xsacc[tid];
+    if (v != 0.0) atomicAdd(&xs[(size_t)k * D + i0 + tid], v);
+  }
+}
+
 // Sufficient statistics, diagonal: CTA covers 64 clusters x 64 dimensions.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -419,6 +622,7 @@ sstat_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
   const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < N) ? r0 + rows_per_cta : N;
   T c[4][4], s1[4][4], s2[4][4];
+  double S1[4][4], S2[4][4];  // fp32 chunk sums are folded into fp64 every NC rows
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
@@ -427,6 +631,8 @@ sstat_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
       c[a][b] = (k < K && d < D) ? cen[(size_t)k * D + d] : (T)0;
       s1[a][b] = 0;
       s2[a][b] = 0;
+      S1[a][b] = 0;
+      S2[a][b] = 0;
     }
   for (int64_t t0 = r0; t0 < r1; t0 += NC) {
     __syncthreads();
@@ -466,6 +672,15 @@ sstat_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
           s2[a][b] = fma(t, xc, s2[a][b]);
         }
     }
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        S1[a][b] += (double)s1[a][b];
+        S2[a][b] += (double)s2[a][b];
+        s1[a][b] = 0;
+        s2[a][b] = 0;
+      }
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
@@ -473,8 +688,8 @@ sstat_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
     for (int b = 0; b < 4; ++b) {
       const int k = kt0 + ty * 4 + a, d = dt0 + tx * 4 + b;
       if (k < K && d < D) {
-        if (s1[a][b] != (T)0) atomicAdd(&xs[(size_t)k * D + d], (double)s1[a][b]);
-        if (s2[a][b] != (T)0) atomicAdd(&S[(size_t)k * D + d], (double)s2[a][b]);
+        if (S1[a][b] != 0.0) atomicAdd(&xs[(size_t)k * D + d], S1[a][b]);
+        if (S2[a][b] != 0.0) atomicAdd(&S[(size_t)k * D + d], S2[a][b]);
       }
     }
 }
@@ -862,6 +1077,62 @@ cudaError_t sstat_full(cudaStream_t st, const T* X, int64_t N, int D, int64_t ld
   return cudaGetLastError();
 }
 
+
+template <typename T>
+cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
+                     int32_t* blockcnt) {
+  if (N <= 0) return cudaSuccess;
+  nz_count_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, blockcnt);
+  return cudaGetLastError();
+}
+cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total) {
+  nz_scan_kernel<<<K, kThreads, 0, st>>>(blockcnt, nblocks, K, total);
+  return cudaGetLastError();
+}
+template <typename T>
+cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq) {
+  if (N <= 0) return cudaSuccess;
+  nz_fill_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, blockoff, koff,
+                                                                            lrow, lq);
+  return cudaGetLastError();
+}
+int64_t nz_blocks(int64_t N) { return (N + kNzBlock - 1) / kNzBlock; }
+
+template <typename T, int TN>
+static cudaError_t launch_gather_full(cudaStream_t st, dim3 grid, const T* X, int D, int64_t ldx, const int32_t* lrow,
+                                      const T* lq, const long long* koff, const long long* kcnt, int DP, const T* cen,
+                                      int nb, double* xs, double* S) {
+  constexpr int BW = 16 * TN, TMS = sizeof(T) == 8 ? 16 : 32;
+  size_t smem = (((size_t)(2 * TMS * BW + TMS) * sizeof(T) + TMS * 4 + 15) & ~(size_t)15);
+  if (sizeof(T) == 4) smem += sizeof(double) * ((size_t)TN * TN * kThreads + BW);
+  auto kern = sstat_gather_full_kernel<T, TN>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, kThreads, smem, st>>>(X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+  return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
+                              const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
+                              double* xs, double* S) {
+  if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  const int DP = full_dp(D);
+  if (DP == 0) return cudaErrorInvalidValue;
+  const int tn = DP >= 128 ? 8 : DP / 16;
+  const int nb = (D + 16 * tn - 1) / (16 * tn);
+  const long long chunks = (maxcnt + kGatherChunk - 1) / kGatherChunk;
+  if (chunks > 2147483647LL || K > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)chunks, K, nb * nb);
+  switch (tn) {
+    case 1: return launch_gather_full<T, 1>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+    case 2: return launch_gather_full<T, 2>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+    case 4: return launch_gather_full<T, 4>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+    default: return launch_gather_full<T, 8>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+  }
+}
+
 template <typename T>
 cudaError_t sstat_diag(cudaStream_t st, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid, const T* q,
                        int64_t ldq, int K, const T* cen, const uint8_t* act, double* xs, double* S) {
@@ -880,7 +1151,7 @@ cudaError_t colsum(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, c
   if (N <= 0 || K <= 0) return cudaSuccess;
   int kw = 1;
   while (kw < K && kw < kThreads) kw <<= 1;
-  const int rpc = 16384;
+  const int rpc = 2048;
   const int64_t chunks = (N + rpc - 1) / rpc;
   colsum_kernel<T><<<(unsigned)chunks, kThreads, 0, st>>>(q, ldq, N, K, gid, kw, rpc, Njk);
   return cudaGetLastError();
@@ -995,6 +1266,13 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
   template cudaError_t sstat_diag<T>(cudaStream_t, const T*, int64_t, int, int64_t, const int32_t*, const T*,         \
                                      int64_t, int, const T*, const uint8_t*, double*, double*);                       \
   template cudaError_t colsum<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, double*);             \
+  template cudaError_t nz_count<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,     \
+                                   int32_t*);                                                                         \
+  template cudaError_t nz_fill<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,      \
+                                  const int32_t*, const long long*, int32_t*, T*);                                    \
+  template cudaError_t sstat_gather_full<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \
+                                            const long long*, const long long*, long long, int, const T*, double*,   \
+                                            double*);                                                                 \
   template cudaError_t convert_rows<T>(cudaStream_t, const double*, int64_t, int, int64_t, int, const double*, T*,    \
                                        int64_t);                                                                      \
   template cudaError_t convert_f32<T>(cudaStream_t, const float*, int64_t, int, int64_t, const double*, T*, int64_t); \

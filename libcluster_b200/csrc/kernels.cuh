@@ -49,6 +49,21 @@ cudaError_t sstat_diag(cudaStream_t st, const T* X, int64_t N, int D, int64_t ld
 template <typename T>
 cudaError_t colsum(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, double* Njk);
 
+// Non-zero responsibilities as per-cluster (row, q) lists and the full-covariance
+// statistics over those lists (work proportional to nnz(q), not N*K).
+int64_t nz_blocks(int64_t N);  // row blocks used by nz_count / nz_fill
+template <typename T>
+cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
+                     int32_t* blockcnt /* [nz_blocks][K] */);
+cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total /* [K] */);
+template <typename T>
+cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq);
+template <typename T>
+cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
+                              const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
+                              double* xs, double* S);
+
 // ---- data movement / labels / split bookkeeping ---------------------------
 // dst[n][d] = T(src[n][d] - mean[d]) from a staged block of doubles in either order
 template <typename T>

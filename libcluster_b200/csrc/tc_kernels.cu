@@ -39,21 +39,17 @@ namespace {
 
 constexpr int kD = 128;
 constexpr int kTM = 128;
-constexpr uint32_t kXBytes = kTM * kD * 4;        // 65536
 constexpr uint32_t kAPart = kTM * 128;            // one fp16 [128 x 64] swizzled block: 16384
-constexpr uint32_t kABytes = 4 * kAPart;          // kb0 hi, kb0 lo, kb1 hi, kb1 lo
-constexpr uint32_t kBBlob = kTcBlobBytes;         // 49152: kb0 hi(16K) lo(16K) kb1 hi(8K) lo(8K)
-constexpr uint32_t kOffX = 0;
-constexpr uint32_t kOffA = kOffX + kXBytes;
-constexpr uint32_t kOffB = kOffA + kABytes;
-constexpr uint32_t kOffBar = kOffB + 2 * kBBlob;  // 229376
+constexpr uint32_t kBBlob = kTcBlobBytes;         // B: kb0 hi(16K) lo(16K) kb1 hi(8K) lo(8K) | mhi (512) | -s*mlo (512)
+constexpr uint32_t kOffMean = 49152;              // offset of the mean vectors inside a stage
+constexpr int kStages = 4;
+constexpr uint32_t kOffBar = kStages * kBBlob;    // 200704
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
-constexpr int kThreadsTc = 512;
-constexpr uint32_t kTmemCols = 256;
+constexpr int kThreadsTc = 512;               // 4 control + 4 epilogue + 8 operand-builder warps
+constexpr uint32_t kTmemCols = 512;               // D0 [0,128) D1 [128,256) A0 hi/lo [256,384) A1 hi/lo [384,512)
 
 // barrier slots (8 bytes each) after kOffBar
-enum { BX_FULL = 0, BX_EMPTY, BA_FULL0, BA_FULL1, BA_EMPTY0, BA_EMPTY1, BB_FULL0, BB_FULL1, BB_EMPTY0, BB_EMPTY1,
-       BT_FULL0, BT_FULL1, BT_EMPTY0, BT_EMPTY1, B_COUNT };
+enum { BB_FULL0 = 0, BB_EMPTY0 = 4, BA_FULL00 = 8 /* [buf][kb] */, BA_EMPTY00 = 12, BT_FULL0 = 16, BT_EMPTY0 = 18, B_COUNT = 20 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -89,21 +85,29 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (fp16 in, fp32 accumulate)
-__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
+// D[tmem] (+)= A[tmem] * B[smem desc], kind::f16 (fp16 in, fp32 accumulate)
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  if (accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
+        : "memory");
+  }
 }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -119,7 +123,8 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
 __device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
   return (1u << 4) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+// 32 consecutive accumulator columns of this thread's TMEM lane, squared and summed (packed f32x2 FMAs)
+__device__ __forceinline__ float tmem_sumsq32(uint32_t taddr) {
   uint32_t r[32];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -132,26 +137,67 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  unsigned long long acc0 = 0ull, acc1 = 0ull;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 32; i += 4) {
+    unsigned long long p0, p1;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p0) : "r"(r[i]), "r"(r[i + 1]));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(p1) : "r"(r[i + 2]), "r"(r[i + 3]));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc0) : "l"(p0));
+    asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc1) : "l"(p1));
+  }
+  uint32_t a, b, c, d;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(acc0));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(c), "=r"(d) : "l"(acc1));
+  return (__uint_as_float(a) + __uint_as_float(b)) + (__uint_as_float(c) + __uint_as_float(d));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
 }
 
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) {
+  unsigned long long A = *reinterpret_cast<unsigned long long*>(&a), B = *reinterpret_cast<unsigned long long*>(&b), C;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(C) : "l"(A), "l"(B));
+  return *reinterpret_cast<float2*>(&C);
+}
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+// (x - mh) * s + nml on two lanes at once; returns the pair
+__device__ __forceinline__ float2 centre_scale2(float2 x, float2 mh, float2 s2, float2 nml) {
+  unsigned long long X = *reinterpret_cast<unsigned long long*>(&x), M = *reinterpret_cast<unsigned long long*>(&mh),
+                     S = *reinterpret_cast<unsigned long long*>(&s2), L = *reinterpret_cast<unsigned long long*>(&nml), T, A;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(T) : "l"(X), "l"(M));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(A) : "l"(T), "l"(S), "l"(L));
+  return *reinterpret_cast<float2*>(&A);
+}
 
 __global__ void __launch_bounds__(kThreadsTc, 1)
 estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __restrict__ gid, int K,
-                   const uint8_t* __restrict__ blob, const float* __restrict__ mhi, const float* __restrict__ mlo,
-                   const float* __restrict__ ascale, const float* __restrict__ inv_t2, const float* __restrict__ chat,
-                   const float* __restrict__ lw, const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq,
-                   double* __restrict__ Fz, unsigned* __restrict__ err) {
+                   const uint8_t* __restrict__ blob, const float* __restrict__ ascale,
+                   const float* __restrict__ inv_t2, const float* __restrict__ chat, const float* __restrict__ lw,
+                   const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq, double* __restrict__ Fz,
+                   unsigned* __restrict__ err) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
-  const uint32_t sX = sbase + kOffX, sA = sbase + kOffA, sB = sbase + kOffB, sBar = sbase + kOffBar;
+  const uint32_t sB = sbase, sBar = sbase + kOffBar;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kOffBar + 8 * B_COUNT);
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
 
@@ -159,20 +205,18 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   const int64_t ntiles = (N + kTM - 1) / kTM;
 
   if (threadIdx.x == 0) {
-    mbar_init(bar(BX_FULL), 1);
-    mbar_init(bar(BX_EMPTY), 8);
-    mbar_init(bar(BA_FULL0), 4);
-    mbar_init(bar(BA_FULL1), 4);
-    mbar_init(bar(BA_EMPTY0), 1);
-    mbar_init(bar(BA_EMPTY1), 1);
-    mbar_init(bar(BB_FULL0), 1);
-    mbar_init(bar(BB_FULL1), 1);
-    mbar_init(bar(BB_EMPTY0), 1);
-    mbar_init(bar(BB_EMPTY1), 1);
-    mbar_init(bar(BT_FULL0), 1);
-    mbar_init(bar(BT_FULL1), 1);
-    mbar_init(bar(BT_EMPTY0), 4);
-    mbar_init(bar(BT_EMPTY1), 4);
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(bar(BB_FULL0 + i), 1);
+      mbar_init(bar(BB_EMPTY0 + i), 9);  // MMA commit + 8 builder warps
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(BA_FULL00 + i), 4);  // 4 lane quadrants
+      mbar_init(bar(BA_EMPTY00 + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(BT_FULL0 + i), 1);
+      mbar_init(bar(BT_EMPTY0 + i), 4);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -187,62 +231,68 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  // Register budget per role (64K registers / SM): the control warps and the epilogue
+  // hand registers to the operand builders, which keep 64 fp32 of X per thread.
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
     // ------------------------------------------------------------ producer --
-    if (lane == 0) {
-      uint32_t it = 0, bcount = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-        const int64_t n0 = tile * kTM;
-        const uint32_t rows = (uint32_t)((N - n0 < kTM) ? (N - n0) : kTM);
-        mbar_wait(bar(BX_EMPTY), (it & 1) ^ 1, err);
-        mbar_expect_tx(bar(BX_FULL), rows * kD * 4);
-        bulk_g2s(sX, X + n0 * kD, rows * kD * 4, bar(BX_FULL));
-        for (int k = 0; k < K; ++k, ++bcount) {
-          const uint32_t st = bcount & 1, ph = (bcount >> 1) & 1;
+    if (warp == 0 && lane == 0) {
+      uint32_t cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int k = 0; k < K; ++k, ++cnt) {
+          const uint32_t st = cnt % kStages, ph = (cnt / kStages) & 1;
           mbar_wait(bar(BB_EMPTY0 + st), ph ^ 1, err);
           mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
           bulk_g2s(sB + st * kBBlob, blob + (size_t)k * kBBlob, kBBlob, bar(BB_FULL0 + st));
         }
       }
     }
-  } else if (warp == 1) {
     // ---------------------------------------------------------- MMA issuer --
-    if (lane == 0) {
+    // The whole warp runs the loop so that addresses and descriptors live in uniform
+    // registers; only the tcgen05 instructions themselves are issued by one elected lane.
+    if (warp == 1) {
       uint32_t cnt = 0;  // clusters processed so far (all rings advance once per cluster)
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int k = 0; k < K; ++k, ++cnt) {
+          const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
           const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
           mbar_wait(bar(BT_EMPTY0 + st), ph ^ 1, err);
-          mbar_wait(bar(BB_FULL0 + st), ph, err);
-          const uint32_t sBk = sB + st * kBBlob;
+          mbar_wait(bar(BB_FULL0 + bs), bph, err);
+          const uint32_t sBk = sB + bs * kBBlob;
+          const uint32_t a_hi0 = tmem_base + 256 + st * 128, a_lo0 = a_hi0 + 64;
+          const uint32_t d0 = tmem_base + st * 128;
 #pragma unroll
           for (int kb = 0; kb < 2; ++kb) {
-            mbar_wait(bar(BA_FULL0 + kb), cnt & 1, err);
+            mbar_wait(bar(BA_FULL00 + 2 * st + kb), ph, err);
             tc_fence_after();
-            const uint32_t a_hi = sA + (uint32_t)kb * 2 * kAPart, a_lo = a_hi + kAPart;
             const uint32_t b_hi = sBk + (kb == 0 ? 0u : 2 * kAPart);
             const uint32_t b_lo = b_hi + (kb == 0 ? kAPart : kAPart / 2);
+            const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
+            if (elect_one()) {
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
-              const uint32_t c = 4 * kb + c4, nc = 128 - 16 * c;
-              const uint32_t rowoff = (16 * c - 64 * kb) * 128;  // first needed row inside the stored block
-              const uint32_t koff = 32 * c4;                      // 16 fp16 along K inside the 128-byte row
-              const uint32_t d = tmem_base + st * 128 + 16 * c;
-              const uint32_t id = umma_idesc(nc);
-              const uint64_t dah = umma_desc(a_hi + koff), dal = umma_desc(a_lo + koff);
-              const uint64_t dbh = umma_desc(b_hi + rowoff + koff), dbl = umma_desc(b_lo + rowoff + koff);
-              tc_mma_f16(d, dah, dbh, id, (kb | c4) ? 1u : 0u);
-              tc_mma_f16(d, dah, dbl, id, 1u);
-              tc_mma_f16(d, dal, dbh, id, 1u);
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const uint32_t c = 4 * kb + c4, nc = 128 - 16 * c;
+                // first needed row of the stored block and the 16 fp16 along K inside the 128-byte row
+                const uint64_t off = (uint64_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
+                const uint32_t id = umma_idesc(nc);
+                tc_mma_f16_ts(d0 + 16 * c, a_hi0 + 8 * c, dbh0 + off, id, (kb | c4) ? 1u : 0u);
+                tc_mma_f16_ts(d0 + 16 * c, a_hi0 + 8 * c, dbl0 + off, id, 1u);
+                tc_mma_f16_ts(d0 + 16 * c, a_lo0 + 8 * c, dbh0 + off, id, 1u);
+              }
+              tc_commit(bar(BA_EMPTY00 + 2 * st + kb));
             }
-            tc_commit(bar(BA_EMPTY0 + kb));
+            __syncwarp();
           }
-          tc_commit(bar(BB_EMPTY0 + st));
-          tc_commit(bar(BT_FULL0 + st));
+          if (elect_one()) {
+            tc_commit(bar(BB_EMPTY0 + bs));
+            tc_commit(bar(BT_FULL0 + st));
+          }
+          __syncwarp();
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
     // ------------------------------------------------------------- epilogue --
     const int ew = warp - 4;
     double fz = 0;
@@ -261,12 +311,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         tc_fence_after();
         float s = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          float v[32];
-          tmem_ld32(tmem_base + ((uint32_t)(ew * 32) << 16) + st * 128 + 32 * cc, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) s = fmaf(v[i], v[i], s);
-        }
+        for (int cc = 0; cc < 4; ++cc) s += tmem_sumsq32(tmem_base + ((uint32_t)(ew * 32) << 16) + st * 128 + 32 * cc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BT_EMPTY0 + st));
@@ -296,41 +341,63 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     }
     for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
     if (lane == 0) atomicAdd(Fz, fz);
-  } else if (warp >= 8) {
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     // ------------------------------------------------------ operand builders --
-    const int bw = warp - 8, kb = bw >> 2, sub = bw & 3;
-    const int d = 64 * kb + 2 * lane;
-    const float* xs = reinterpret_cast<const float*>(sgen + kOffX);
-    const uint32_t a_hi = sA + (uint32_t)kb * 2 * kAPart, a_lo = a_hi + kAPart;
-    uint32_t it = 0, cnt = 0;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      mbar_wait(bar(BX_FULL), it & 1, err);
-      for (int k = 0; k < K; ++k, ++cnt) {
-        const float2 mh = *reinterpret_cast<const float2*>(mhi + (size_t)k * kD + d);
-        const float2 ml = *reinterpret_cast<const float2*>(mlo + (size_t)k * kD + d);
-        const float sc = ascale[k];
-        mbar_wait(bar(BA_EMPTY0 + kb), (cnt & 1) ^ 1, err);
-#pragma unroll 8
-        for (int r = 0; r < 32; ++r) {
-          const int nrow = sub * 32 + r;
-          const float2 x = *reinterpret_cast<const float2*>(xs + nrow * kD + d);
-          const float a0 = ((x.x - mh.x) - ml.x) * sc;
-          const float a1 = ((x.y - mh.y) - ml.y) * sc;
-          const uint32_t hi = pack_f16x2_sat(a0, a1);
-          const __half2 hh = *reinterpret_cast<const __half2*>(&hi);
-          const float2 hf = __half22float2(hh);
-          const uint32_t lo = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
-          const uint32_t off = (uint32_t)nrow * 128u + ((((uint32_t)lane >> 2) ^ ((uint32_t)nrow & 7u)) << 4) +
-                               (((uint32_t)lane & 3u) << 2);
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_hi + off), "r"(hi) : "memory");
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_lo + off), "r"(lo) : "memory");
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BA_FULL0 + kb));
+    // thread <-> one point (TMEM lane); its 64 dims of K block kb stay in registers for the whole tile
+    const int quad = warp & 3, kb = (warp - 8) >> 2;
+    const int row = 32 * quad + lane;
+    uint32_t cnt = 0;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t n = tile * kTM + row;
+      float4 x[16];
+      if (n < N) {
+        const float4* src = reinterpret_cast<const float4*>(X + n * kD + 64 * kb);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = __ldg(src + j);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BX_EMPTY));
+      for (int k = 0; k < K; ++k, ++cnt) {
+        const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
+        const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
+        const float sc = ascale[k];
+        const float2 s2 = make_float2(sc, sc);
+        mbar_wait(bar(BB_FULL0 + bs), bph, err);
+        mbar_wait(bar(BA_EMPTY00 + 2 * st + kb), ph ^ 1, err);
+        tc_fence_after();
+        const float4* mh4 = reinterpret_cast<const float4*>(sgen + bs * kBBlob + kOffMean + 256 * kb);
+        const float4* nl4 = reinterpret_cast<const float4*>(sgen + bs * kBBlob + kOffMean + 512 + 256 * kb);
+        const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 256 + st * 128 + 32 * kb;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t rh[16], rl[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 xv = x[8 * h + j], mh = mh4[8 * h + j], nl = nl4[8 * h + j];
+            const float2 a01 = centre_scale2(make_float2(xv.x, xv.y), make_float2(mh.x, mh.y), s2, make_float2(nl.x, nl.y));
+            const float2 a23 = centre_scale2(make_float2(xv.z, xv.w), make_float2(mh.z, mh.w), s2, make_float2(nl.z, nl.w));
+            const uint32_t h01 = pack_f16x2_sat(a01.x, a01.y), h23 = pack_f16x2_sat(a23.x, a23.y);
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+            rh[2 * j] = h01;
+            rh[2 * j + 1] = h23;
+            const float2 r01 = sub2(a01, f01), r23 = sub2(a23, f23);
+            rl[2 * j] = pack_f16x2_sat(r01.x, r01.y);
+            rl[2 * j + 1] = pack_f16x2_sat(r23.x, r23.y);
+          }
+          tmem_st16(tA + 16 * h, rh);
+          tmem_st16(tA + 64 + 16 * h, rl);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(BA_FULL00 + 2 * st + kb));
+          mbar_arrive(bar(BB_EMPTY0 + bs));
+        }
+      }
     }
   }
 
@@ -346,16 +413,15 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
 
 cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
-                        const uint8_t* blob, const float* mhi, const float* mlo, const float* ascale,
-                        const float* inv_t2, const float* chat, const float* lw, const uint8_t* act, float* q,
-                        int64_t ldq, double* Fz, unsigned* err) {
+                        const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
+                        const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err) {
   if (N <= 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (N + kTM - 1) / kTM;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  estep_tc128_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, mhi, mlo, ascale, inv_t2, chat, lw, act,
-                                                           q, ldq, Fz, err);
+  estep_tc128_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q, ldq,
+                                                           Fz, err);
   return cudaGetLastError();
 }
 
@@ -363,8 +429,16 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
 // i >= d, split into fp16 hi/lo and laid out exactly as the kernel's shared
 // memory expects (row pitch 128 B = 64 fp16 of one K block, 16-byte chunks
 // XOR-swizzled with row % 8; K block 1 stores rows 64..127 only).
-void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */, double bscale, uint8_t* out) {
+void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */, double bscale,
+                     const double* mean_rel /* [128] cluster mean minus the data centre */, double ascale, uint8_t* out) {
   for (uint32_t i = 0; i < kBBlob; ++i) out[i] = 0;
+  float* mh = reinterpret_cast<float*>(out + kOffMean);
+  float* nl = mh + 128;
+  for (int d = 0; d < 128; ++d) {
+    const float hi = (float)mean_rel[d];
+    mh[d] = hi;
+    nl[d] = (float)(-(mean_rel[d] - (double)hi) * ascale);
+  }
   for (int kbk = 0; kbk < 2; ++kbk) {
     const uint32_t base_hi = kbk == 0 ? 0u : 2 * kAPart;
     const uint32_t base_lo = base_hi + (kbk == 0 ? kAPart : kAPart / 2);

@@ -7,17 +7,16 @@
 namespace lcb {
 namespace dev {
 
-constexpr uint32_t kTcBlobBytes = 49152;  // pre-swizzled fp16 hi/lo operand of one cluster
+constexpr uint32_t kTcBlobBytes = 50176;  // pre-swizzled fp16 hi/lo operand of one cluster + its mean (hi, -s*lo)
 
 // true when the fp32 engine can run the full-covariance E step on the tensor cores
 bool tc_supported(int D, int64_t ldx);
 
 cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
-                        const uint8_t* blob, const float* mhi, const float* mlo, const float* ascale,
-                        const float* inv_t2, const float* chat, const float* lw, const uint8_t* act, float* q,
-                        int64_t ldq, double* Fz, unsigned* err);
+                        const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
+                        const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err);
 
-void tc_pack_cluster(const double* R, double bscale, uint8_t* out);
+void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
 
 }  // namespace dev
 }  // namespace lcb
