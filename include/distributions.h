@@ -180,9 +180,12 @@ class GaussWish : public ClusterDist {
     return m;
   }
   Eigen::MatrixXd getcov() const {
-    Eigen::Matrix<double, Eigen::Dynamic, Eigen::Dynamic, Eigen::RowMajor> c(D, D);
+    std::vector<double> c((size_t)D * D);  // row-major from the C ABI
     lcb_cluster_getcov(h_, c.data());
-    return c;
+    Eigen::MatrixXd out(D, D);
+    for (unsigned i = 0; i < D; ++i)
+      for (unsigned j = 0; j < D; ++j) out(i, j) = c[(size_t)i * D + j];
+    return out;
   }
 };
 

@@ -6,13 +6,16 @@
  * cpu_baseline / --impl reference legs of bench.py may load it.  It is never
  * linked into, imported by, or used as a fallback for the product library.
  *
- * PARITY PINNING: the reference (dsteinberg/libcluster @ c877625) ships no
- * golden vectors and no numeric assertions.  This
- * restatement is pinned instead against the *reference's own sources* compiled
- * under oracle/refbuild (see oracle/Makefile target `ref`, oracle/_ref/) with a
- * minimal stand-in for the absent third-party headers (Eigen 3, Boost.Math);
- * where that build is unavailable the header of tests/golden/README says
- * "parity unpinned" and only the cross-check with oracle/np_oracle.py holds.
+ * PARITY PINNING: the reference (dsteinberg/libcluster @ c877625) ships no golden
+ * vectors and no numeric assertions.  This restatement
+ * is pinned against the REFERENCE'S OWN SOURCES instead: `make -C oracle ref`
+ * compiles /root/reference/src/{cluster,distributions,probutils,comutils}.cpp
+ * where they lie into oracle/_ref/libcluster_ref.so, against minimal stand-ins
+ * for the absent third-party headers (oracle/refshim: Eigen/Dense,
+ * boost/math/special_functions.hpp).  tests/test_reference_pin.py requires this
+ * file to reproduce that library (F, K, qZ, posteriors; 1e-12) on the reference's
+ * test fixture for all six learnXXX, on direct vbem<W,C>() calls and on split /
+ * sparse runs; oracle/np_oracle.py is an independent third opinion.
  *
  * Every function cites the reference file:line it follows (paths relative to
  * /root/reference).  Storage here is plain row-major double arrays; no Eigen.

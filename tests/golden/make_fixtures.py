@@ -64,12 +64,17 @@ def main():
         assert np.allclose([t[0] for t in trn], Ft, rtol=1e-9, atol=0), name
         assert abs(F - Fn) <= 1e-9 * abs(F), (name, F, Fn)
         assert np.abs(q - qn).max() < 1e-9, name
+        from oracle import pyref
+        if pyref.available() or pyref.build():      # the reference's own sources (oracle/_ref)
+            r = pyref.learn(mid, groups)
+            assert r.K == m.K and abs(r.F - F) <= 1e-12 * abs(F), (name, r.F, F)
+            assert np.abs(np.concatenate(r.qZ, 0) - q).max() < 1e-12, name
         means = np.stack([m.cluster(k)["m"] for k in range(m.K)])
         covs = np.stack([m.cluster(k)["iW"] / m.cluster(k)["nu"] for k in range(m.K)])
         elogw = np.stack([m.weights(j)[0] for j in range(len(groups))])
         np.savez(os.path.join(OUT, "golden_%s.npz" % name), F=F, K=m.K, qZ=q, trace_F=Ft,
                  trace_K=Kt, means=means, covs=covs, Elogweight=elogw)
-        print("%-12s K=%d F=%.10f iters=%d  (C oracle == numpy mirror)" % (name, m.K, F, len(Ft)))
+        print("%-12s K=%d F=%.10f iters=%d  (C oracle == numpy mirror == reference build)" % (name, m.K, F, len(Ft)))
 
 
 if __name__ == "__main__":
