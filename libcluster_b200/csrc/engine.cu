@@ -100,7 +100,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
@@ -360,6 +360,7 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
   }
   if (prec_ == kF32) upload_rows<float>(main_, X, Nj, ld, J, layout, centre_);
   else upload_rows<double>(main_, X, Nj, ld, J, layout, centre_);
+  measure_absmax(main_);
   clusters_.clear();
   weights_.clear();
   model_ = -1;
@@ -411,6 +412,7 @@ void Engine::set_data_device_f32(const float* X, int64_t N, int D, int64_t ld, c
     Nj_[0] = N;
   }
   sync();
+  measure_absmax(main_);
   clusters_.clear();
   weights_.clear();
   model_ = -1;
@@ -420,6 +422,26 @@ int64_t Engine::num_rows(int j) const {
   if (j < 0) return main_.N;
   if (j >= (int)Nj_.size()) return -1;
   return Nj_[j];
+}
+
+// max |x| of the resident (centred) data over all ranks: no product of the fp16 operand
+// scale with a data value may overflow half precision in the tensor-core scatter
+void Engine::measure_absmax(const View& v) {
+  reserve(d_err_, 16);
+  check(cudaMemsetAsync(d_err_.p, 0, 16, stream_), "memset");
+  const int64_t n = v.N * v.ldx;
+  if (prec_ == kF32) check(dev::absmax<float>(stream_, (const float*)v.X, n, (unsigned*)d_err_.p + 1), "absmax");
+  else check(dev::absmax<double>(stream_, (const double*)v.X, n, (unsigned*)d_err_.p + 1), "absmax");
+  unsigned bits = 0;
+  check(cudaMemcpyAsync(&bits, (unsigned*)d_err_.p + 1, 4, cudaMemcpyDeviceToHost, stream_), "D2H absmax");
+  sync();
+  float f;
+  std::memcpy(&f, &bits, 4);
+  std::vector<double> slots((size_t)world_, 0.0);
+  slots[(size_t)rank_] = (double)f;
+  allreduce_host(slots.data(), world_);
+  xabs_max_ = 0;
+  for (double sv : slots) xabs_max_ = std::max(xabs_max_, sv);
 }
 
 // ------------------------------------------------------------ VB iteration --
@@ -533,8 +555,20 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
         void* lq = (unsigned char*)d_list_.p + rows_bytes;
         if (prec_ == kF32) {
           check(dev::nz_fill<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (float*)lq), "nz_fill");
-          ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
-                                             maxcnt, K, (const float*)d_cen_.p, d_xs, d_S);
+          if (use_tc_ && dev::tc_supported(D, v.ldx)) {
+            // power-of-two operand scale: scale * max|x - c| <= 2^14 for every row of the data set
+            double cmax = 0;
+            for (int k = 0; k < K; ++k)
+              for (int d = 0; d < D; ++d) cmax = std::max(cmax, std::fabs(craw[(size_t)k * D + d] - centre_[d]));
+            const double span = std::max(xabs_max_ + cmax, 1e-30);
+            const float scale = (float)std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(16384.0 / span)))));
+            reserve(d_err_, 16);
+            ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, maxcnt, K,
+                                  (const float*)d_cen_.p, scale, d_xs, d_S, (unsigned*)d_err_.p);
+          } else {
+            ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
+                                               maxcnt, K, (const float*)d_cen_.p, d_xs, d_S);
+          }
         } else {
           check(dev::nz_fill<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (double*)lq), "nz_fill");
           ke = dev::sstat_gather_full<double>(stream_, (const double*)v.X, D, v.ldx, lrow, (const double*)lq, d_koff,
@@ -760,6 +794,25 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
     else centres[k] = centre_;
   }
   hints_first_ = false;
+  // Fresh clusters without a hint (caller-supplied responsibilities): one preliminary statistics pass
+  // about the data centre gives their weighted means, which then serve as centres -- the statistics
+  // are only as accurate as the centre is close to the cluster (section 6 of DESIGN.md).
+  bool blind = false;
+  for (int k = 0; k < K; ++k) {
+    const bool have_hint = k < (int)hints.size() && (int)hints[k].size() == D;
+    if (!(clusters[k].getN() > 0) && !have_hint) blind = true;
+  }
+  if (blind && K > 1) {
+    std::vector<ClusterPost> probe;
+    for (int k = 0; k < K; ++k) probe.emplace_back(ckind_, prior_, D);
+    std::vector<WeightPost> wprobe(weights);
+    sphase(v, wprobe, probe, centres);
+    for (int k = 0; k < K; ++k)
+      if (probe[k].N_s() > 0) {
+        centres[k] = probe[k].x_s();
+        for (int d = 0; d < D; ++d) centres[k][d] /= probe[k].N_s();
+      }
+  }
   for (int k = 0; k < K; ++k) clusters[k].clearobs();
   sphase(v, weights, clusters, centres);
   // VBM for the clusters (cluster.cpp:215-217 runs this loop under OpenMP as well)
@@ -1230,6 +1283,8 @@ void Engine::op_addobs(ClusterPost& c, const double* qk, const double* X, int64_
   const int saved_ck = ckind_, saved_wk = wkind_;
   const bool saved_sparse = sparse_;
   std::vector<uint8_t> saved_act = act_;
+  const int saved_world = world_;
+  const double saved_absmax = xabs_max_;
   main_ = View();
   View tmp;
   try {
@@ -1261,23 +1316,19 @@ void Engine::op_addobs(ClusterPost& c, const double* qk, const double* X, int64_
     std::vector<WeightPost> w(1, WeightPost(kDirichlet, -1.0));
     std::vector<ClusterPost> cl(1, ClusterPost(c.kind(), c.getprior(), D));
     std::vector<std::vector<double>> cen(1, c.getN() > 0 ? c.mean() : centre_);
-    const int sw = world_;
     world_ = 1;  // operator calls are local
-    try {
-      sphase(tmp, w, cl, cen);
-    } catch (...) {
-      world_ = sw;
-      throw;
-    }
-    world_ = sw;
+    measure_absmax(tmp);
+    sphase(tmp, w, cl, cen);
     c.add_stats(cl[0].N_s(), cl[0].x_s().data(), cl[0].xx_s().data());
   } catch (...) {
     free_view(tmp);
     main_ = saved; centre_ = saved_centre; ckind_ = saved_ck; wkind_ = saved_wk; sparse_ = saved_sparse; act_ = saved_act;
+    world_ = saved_world; xabs_max_ = saved_absmax;
     throw;
   }
   free_view(tmp);
   main_ = saved; centre_ = saved_centre; ckind_ = saved_ck; wkind_ = saved_wk; sparse_ = saved_sparse; act_ = saved_act;
+  world_ = saved_world; xabs_max_ = saved_absmax;
 }
 
 void Engine::op_eloglike(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, double* out) {

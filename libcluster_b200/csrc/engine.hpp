@@ -109,6 +109,8 @@ class Engine {
   std::vector<int64_t> Nj_;       // local rows per group
   std::vector<double> centre_;    // global column mean subtracted at upload
   int64_t N_total_ = 0;           // rows over all ranks
+  double xabs_max_ = 0;           // max |x - centre| over all rows and ranks (bounds the fp16 operand scale)
+  void measure_absmax(const View& v);
 
   // model state of the current fit
   int model_ = -1, wkind_ = 0, ckind_ = 0;
@@ -124,7 +126,7 @@ class Engine {
   bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
 
   // device scratch
-  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_;
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_, d_err_;
   std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;

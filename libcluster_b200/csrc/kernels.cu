@@ -756,6 +756,15 @@ __global__ void colsum_f32_kernel(const float* __restrict__ src, int64_t rows, i
   }
 }
 
+// max |x| over a buffer (positive floats order like their bit patterns)
+template <typename T> __global__ void absmax_kernel(const T* __restrict__ x, int64_t n, unsigned* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf((float)x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
 template <typename T> __global__ void fill_ones_kernel(T* q, int64_t ldq, int64_t N) {
   for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (int64_t)gridDim.x * blockDim.x)
     q[n * ldq] = (T)1;
@@ -1177,6 +1186,11 @@ cudaError_t colsum_f32(cudaStream_t st, const float* src, int64_t rows, int D, i
   colsum_f32_kernel<<<(unsigned)((rows + rpc - 1) / rpc), 128, 0, st>>>(src, rows, D, ld, rpc, sums);
   return cudaGetLastError();
 }
+template <typename T> cudaError_t absmax(cudaStream_t st, const T* x, int64_t n, unsigned* out_bits) {
+  if (n <= 0) return cudaSuccess;
+  absmax_kernel<T><<<grid_for(n, 256), 256, 0, st>>>(x, n, out_bits);
+  return cudaGetLastError();
+}
 template <typename T> cudaError_t fill_ones(cudaStream_t st, T* q, int64_t ldq, int64_t N) {
   if (N <= 0) return cudaSuccess;
   fill_ones_kernel<T><<<grid_for(N, 256), 256, 0, st>>>(q, ldq, N);
@@ -1277,6 +1291,7 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
                                        int64_t);                                                                      \
   template cudaError_t convert_f32<T>(cudaStream_t, const float*, int64_t, int, int64_t, const double*, T*, int64_t); \
   template cudaError_t fill_ones<T>(cudaStream_t, T*, int64_t, int64_t);                                              \
+  template cudaError_t absmax<T>(cudaStream_t, const T*, int64_t, unsigned*);                                         \
   template cudaError_t labels_to_q<T>(cudaStream_t, const int32_t*, T*, int64_t, int64_t, int);                       \
   template cudaError_t q_from_double<T>(cudaStream_t, const double*, int64_t, int, T*, int64_t);                      \
   template cudaError_t q_to_double<T>(cudaStream_t, const T*, int64_t, int64_t, int, double*, int64_t, int);          \

@@ -74,6 +74,8 @@ cudaError_t convert_f32(cudaStream_t st, const float* src, int64_t rows, int D, 
                         T* dst, int64_t ldx);
 cudaError_t colsum_f32(cudaStream_t st, const float* src, int64_t rows, int D, int64_t ld, double* sums);
 template <typename T> cudaError_t fill_ones(cudaStream_t st, T* q, int64_t ldq, int64_t N);
+// bit pattern of max |x| over n elements, combined into *out_bits with atomicMax (zero it first)
+template <typename T> cudaError_t absmax(cudaStream_t st, const T* x, int64_t n, unsigned* out_bits);
 template <typename T> cudaError_t labels_to_q(cudaStream_t st, const int32_t* lab, T* q, int64_t ldq, int64_t N, int K);
 template <typename T> cudaError_t q_from_double(cudaStream_t st, const double* src, int64_t rows, int K, T* q, int64_t ldq);
 template <typename T>

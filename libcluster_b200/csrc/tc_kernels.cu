@@ -408,6 +408,223 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   }
 }
 
+
+// ===========================================================================
+// sstat_tc128_kernel: centred scatter of one cluster over a chunk of its list of
+// non-zero responsibilities, D == 128:
+//     S_k += sum_r (x_r - c_k) q_r (x_r - c_k)^T ,   xs_k += sum_r q_r (x_r - c_k)
+// as a 128 x 128 x (rows) GEMM on tcgen05: A = s (X - c)^T [dims x rows] lives in
+// TMEM, B = q s (X - c) [dims x rows, rows contiguous] in swizzled shared memory,
+// both split into fp16 (hi, lo) with the three significant products accumulated in
+// one fp32 TMEM accumulator.  s is a power of two that cannot saturate fp16 for any
+// row of the data set (engine: 2^14 / max|x - c|).  A thread owns one dimension
+// (= TMEM lane = B row) and 64 of the 128 rows of a tile; rows are gathered from X
+// through the per-cluster (row, q) lists built by nz_fill.  The accumulator covers
+// at most kScatterChunk rows (<= 128 tensor-core additions per element) before it
+// is added, in fp64, to the global statistics.
+// ===========================================================================
+constexpr int kScatterThreads = 384;  // 4 control warps + 8 builder warps
+constexpr uint32_t kSB_Stage = 65536; // per stage: K block 0 (hi 16K, lo 16K), K block 1 (hi, lo)
+constexpr uint32_t kSOffList = 2 * kSB_Stage;
+constexpr uint32_t kSOffBar = kSOffList + 2 * 128 * 8;
+constexpr uint32_t kSSmemBytes = kSOffBar + 256 + 1024;
+enum { SL_FULL0 = 0, SL_EMPTY0 = 2, SAB_FULL00 = 4 /* [stage][h] */, SAB_EMPTY00 = 8, SACC_FULL = 12, SB_COUNT = 13 };
+
+__global__ void __launch_bounds__(kScatterThreads, 1)
+sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow, const float* __restrict__ lq,
+                   const long long* __restrict__ koff, const long long* __restrict__ kcnt,
+                   const float* __restrict__ cen, float scale, double* __restrict__ xs, double* __restrict__ S,
+                   unsigned* __restrict__ err) {
+  const int k = blockIdx.y;
+  const long long cnt = kcnt[k];
+  const long long l0 = (long long)blockIdx.x * kTcScatterChunk;
+  if (l0 >= cnt) return;
+  const long long l1 = (l0 + kTcScatterChunk < cnt) ? l0 + kTcScatterChunk : cnt;
+  const long long base = koff[k];
+  const int ntile = (int)((l1 - l0 + 127) / 128);
+
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
+  const uint32_t sBar = sbase + kSOffBar;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kSOffBar + 8 * SB_COUNT);
+  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(SL_FULL0 + i), 1);
+      mbar_init(bar(SL_EMPTY0 + i), 8);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(bar(SAB_FULL00 + i), 4);
+      mbar_init(bar(SAB_EMPTY00 + i), 1);
+    }
+    mbar_init(bar(SACC_FULL), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ---- list loader: (row, q) of the next 128 list entries into shared memory ----
+    for (int t = 0; t < ntile; ++t) {
+      const int st = t & 1;
+      mbar_wait(bar(SL_EMPTY0 + st), ((t >> 1) & 1) ^ 1, err);
+      int2* dst = reinterpret_cast<int2*>(sgen + kSOffList + st * 1024);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const long long l = l0 + (long long)t * 128 + e * 32 + lane;
+        int2 v = make_int2(-1, 0);
+        if (l < l1) {
+          v.x = lrow[base + l];
+          v.y = __float_as_int(lq[base + l]);
+        }
+        dst[e * 32 + lane] = v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(SL_FULL0 + st));
+    }
+  } else if (warp == 1) {
+    // ---- MMA issuer ----
+    for (int t = 0; t < ntile; ++t) {
+      const int st = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      const uint32_t a_hi0 = tmem_base + 128 + st * 128, a_lo0 = a_hi0 + 64;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        mbar_wait(bar(SAB_FULL00 + 2 * st + h), ph, err);
+        tc_fence_after();
+        const uint32_t b_hi = sbase + st * kSB_Stage + h * 32768, b_lo = b_hi + 16384;
+        const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
+        const uint32_t id = umma_idesc(128);
+        if (elect_one()) {
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const uint64_t off = (uint64_t)((32 * c4) >> 4);
+            const uint32_t acol = 32 * h + 8 * c4;
+            if (t == 0 && h == 0 && c4 == 0) tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, 0u);
+            else tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, 1u);
+            tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbl0 + off, id, 1u);
+            tc_mma_f16_ts(tmem_base, a_lo0 + acol, dbh0 + off, id, 1u);
+          }
+          tc_commit(bar(SAB_EMPTY00 + 2 * st + h));
+        }
+        __syncwarp();
+      }
+    }
+    if (elect_one()) tc_commit(bar(SACC_FULL));
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ---- builders: thread = dimension i (TMEM lane, B row), half h of the tile's rows ----
+    const int quad = warp & 3, h = (warp - 4) >> 2;
+    const int i = 32 * quad + lane;
+    const float ncs = -cen[(size_t)k * kD + i] * scale;
+    double xs64 = 0.0;
+    for (int t = 0; t < ntile; ++t) {
+      const int st = t & 1;
+      const uint32_t ph = (t >> 1) & 1;
+      mbar_wait(bar(SL_FULL0 + st), ph, err);
+      const int2* lst = reinterpret_cast<const int2*>(sgen + kSOffList + st * 1024) + 64 * h;
+      float a[64];
+#pragma unroll
+      for (int r = 0; r < 64; ++r) {
+        const int row = lst[r].x;
+        a[r] = row >= 0 ? __ldg(X + (size_t)row * kD + i) : 0.f;
+      }
+      float xs32 = 0.f;
+      mbar_wait(bar(SAB_EMPTY00 + 2 * st + h), ph ^ 1, err);
+      tc_fence_after();
+      const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 128 + st * 128 + 32 * h;
+      const uint32_t bRow = sbase + st * kSB_Stage + h * 32768 + (uint32_t)i * 128u;
+#pragma unroll
+      for (int g = 0; g < 2; ++g) {  // 32 rows per group: 16 packed columns of A, 4 chunks of B
+        uint32_t ah[16], al[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t bh[4], bl[4];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const int r = 32 * g + 8 * c + 2 * p;
+            const int2 e0 = lst[r], e1 = lst[r + 1];
+            const float q0 = __int_as_float(e0.y), q1 = __int_as_float(e1.y);
+            const float a0 = e0.x >= 0 ? fmaf(a[r], scale, ncs) : 0.f;
+            const float a1 = e1.x >= 0 ? fmaf(a[r + 1], scale, ncs) : 0.f;
+            const uint32_t hh = pack_f16x2_sat(a0, a1);
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+            ah[4 * c + p] = hh;
+            al[4 * c + p] = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
+            const float v0 = q0 * a0, v1 = q1 * a1;
+            xs32 += v0 + v1;
+            const uint32_t vh = pack_f16x2_sat(v0, v1);
+            const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vh));
+            bh[p] = vh;
+            bl[p] = pack_f16x2_sat(v0 - vf.x, v1 - vf.y);
+          }
+          const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 16384u), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
+        }
+        tmem_st16(tA + 16 * g, ah);
+        tmem_st16(tA + 64 + 16 * g, al);
+      }
+      xs64 += (double)xs32;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(SAB_FULL00 + 2 * st + h));
+        mbar_arrive(bar(SL_EMPTY0 + st));
+      }
+    }
+    const double inv_s = 1.0 / (double)scale;
+    if (xs64 != 0.0) atomicAdd(&xs[(size_t)k * kD + i], xs64 * inv_s);
+    if (h == 0) {
+      // ---- epilogue: accumulator -> fp64 global statistics (S is symmetric: lane i writes column i) ----
+      mbar_wait(bar(SACC_FULL), 0, err);
+      tc_fence_after();
+      const double inv_s2 = inv_s * inv_s;
+      double* Sk = S + (size_t)k * kD * kD;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 32 * cc)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const double v = (double)__uint_as_float(r[jj]) * inv_s2;
+          if (v != 0.0) atomicAdd(&Sk[(size_t)(32 * cc + jj) * kD + i], v);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 }  // namespace
 
 bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
@@ -422,6 +639,20 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   estep_tc128_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q, ldq,
                                                            Fz, err);
+  return cudaGetLastError();
+}
+
+
+cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
+                        const long long* kcnt, long long maxcnt, int K, const float* cen, float scale, double* xs,
+                        double* S, unsigned* err) {
+  if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(sstat_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes);
+  if (e != cudaSuccess) return e;
+  const long long chunks = (maxcnt + kTcScatterChunk - 1) / kTcScatterChunk;
+  if (chunks > 2147483647LL || K > 65535) return cudaErrorInvalidValue;
+  dim3 grid((unsigned)chunks, K);
+  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, cen, scale, xs, S, err);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,13 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err);
 
+// Centred scatter over the per-cluster non-zero lists (see tc_kernels.cu); cen [K][128] is relative to the data
+// centre, scale a power of two with scale * max|x - c| <= 2^14.
+constexpr int kTcScatterChunk = 2048;  // list rows folded into one fp32 accumulator before the fp64 add
+cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
+                        const long long* kcnt, long long maxcnt, int K, const float* cen, float scale, double* xs,
+                        double* S, unsigned* err);
+
 void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
 
 }  // namespace dev
