@@ -310,18 +310,24 @@ def main():
 
     # ---- roofline of the dominant kernel (device-event time, this run) -------
     pk = peaks()
+    tc = (prec == lc.F32 and D == 128 and not os.environ.get("LCB_DISABLE_TC"))
     flops_half = float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
     if e_ms >= s_ms:
-        kname, kms = "estep_full_kernel", e_ms / a.steps
+        kname, kms = ("estep_tc128_kernel" if tc else "estep_full_kernel"), e_ms / a.steps
+        # measured with ncu --set full at N=2M (profiles/ncu_r01_tc_summary.md): dram read+write per point
+        traffic = 756.0 * nloc if tc else None
     else:
-        kname, kms = "sstat_full_kernel", s_ms / a.steps
+        kname, kms = ("nz_count+nz_fill+sstat_tc128_kernel" if tc else "sstat pass"), s_ms / a.steps
+        traffic = None
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach_tf = flops_half / (kms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": kname, "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf, "traffic": None, "peak_source": pk["_source"] + " bf16_tflops_sustained",
-                "kernel_ms": kms, "hbm_frac": (4.0 * D * nloc / (kms * 1e-3) / 1e9) / pk["hbm_gbs"],
+                "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["_source"] + " bf16_tflops_sustained",
+                "kernel_ms": kms, "hbm_frac": (4.0 * (D + K) * nloc / (kms * 1e-3) / 1e9) / pk["hbm_gbs"],
                 "sstat_ms": s_ms / a.steps, "estep_ms": e_ms / a.steps,
-                "note": "algorithmic K*D^2 flops/point for this half of the pass (fp32 SIMT tier)"}
+                "note": "achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
+                        "E-pass kernel; the fp16 hi/lo scheme executes 3 x 0.56 x 2 = 3.4 tensor flop per algorithmic "
+                        "flop, so tensor-pipe utilisation is higher than frac (ncu: profiles/)"}
 
     # ---- e2e: the same step through the C ABI from HOST buffers ---------------
     e2e = None
