@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--model", default="bgmm", choices=["bgmm", "dgmm"], help="bgmm: full covariance (headline); dgmm: diagonal (config 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -64,14 +65,17 @@ def peaks():
 
 
 # ------------------------------------------------------------------ data ---
-def mixture_params(D, K):
-    """means U(-10,10)^D, covariances A A^T / D + 0.5 I, weights Dirichlet(5)."""
+def mixture_params(D, K, diag=False):
+    """means U(-10,10)^D, covariances A A^T / D + 0.5 I (or diag(U(0.5,2))), weights Dirichlet(5)."""
     rng = np.random.default_rng(SEED)
     mu = rng.uniform(-10, 10, size=(K, D))
-    L = np.empty((K, D, D))
-    for k in range(K):
-        A = rng.normal(size=(D, D))
-        L[k] = np.linalg.cholesky(A @ A.T / D + 0.5 * np.eye(D))
+    if diag:
+        L = np.sqrt(rng.uniform(0.5, 2.0, size=(K, D)))     # per-dimension standard deviations
+    else:
+        L = np.empty((K, D, D))
+        for k in range(K):
+            A = rng.normal(size=(D, D))
+            L[k] = np.linalg.cholesky(A @ A.T / D + 0.5 * np.eye(D))
     w = rng.dirichlet(5.0 * np.ones(K))
     return mu, L, w
 
@@ -82,6 +86,8 @@ def gen_chunk_torch(torch, dev, c, rows, D, K, mu_t, L_t, w_t):
     e = torch.randn(rows, D, device=dev, generator=g)
     x = torch.empty(rows, D, device=dev, dtype=torch.float32)
     zl = z.long()
+    if L_t.dim() == 2:                                      # diagonal covariances
+        return (mu_t[zl] + e * L_t[zl]).contiguous(), z
     order = torch.argsort(zl)
     counts = torch.bincount(zl, minlength=K).tolist()
     o = 0
@@ -261,7 +267,8 @@ def main():
         dist.broadcast(idt, 0)
         eng.comm_init_nccl(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
-    mu, L, w = mixture_params(D, K)
+    diag = a.model == "dgmm"
+    mu, L, w = mixture_params(D, K, diag)
     mu_t = torch.tensor(mu, dtype=torch.float32, device=dev)
     L_t = torch.tensor(L, dtype=torch.float32, device=dev)
     w_t = torch.tensor(w, dtype=torch.float32, device=dev)
@@ -275,8 +282,9 @@ def main():
         z[o:o + rows] = zc
     torch.cuda.synchronize()
 
+    MODEL = lc.DGMM if diag else lc.BGMM
     eng.set_data_device(X.data_ptr(), nloc, D, D)
-    eng.model_init(lc.BGMM)
+    eng.model_init(MODEL)
     eng.set_labels_device(z.data_ptr(), K)
 
     def barrier():
@@ -310,8 +318,8 @@ def main():
 
     # ---- roofline of the dominant kernel (device-event time, this run) -------
     pk = peaks()
-    tc = (prec == lc.F32 and D == 128 and not os.environ.get("LCB_DISABLE_TC"))
-    flops_half = float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
+    tc = (prec == lc.F32 and D == 128 and not diag and not os.environ.get("LCB_DISABLE_TC"))
+    flops_half = (3.5 * K * D * nloc) if diag else float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
     if e_ms >= s_ms:
         kname, kms = ("estep_tc128_kernel" if tc else "estep_full_kernel"), e_ms / a.steps
         # measured with ncu --set full at N=2M (profiles/ncu_r01_tc_summary.md): dram read+write per point
@@ -354,8 +362,9 @@ def main():
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if prec == lc.F32 else "f64", "data": "synthetic",
-            "config": {"workload": "VB iteration (SS + M + E + F), learnBGMM pair (Dirichlet, GaussWish full-cov), "
-                       "N=%d D=%d K=%d" % (N, D, K), "rows_per_gpu": nloc, "parallelism": "rows sharded x%d" % world,
+            "config": {"workload": "VB iteration (SS + M + E + F), %s, N=%d D=%d K=%d" % (
+                "learnDGMM pair (Dirichlet, NormGamma diagonal)" if diag else
+                "learnBGMM pair (Dirichlet, GaussWish full-cov)", N, D, K), "rows_per_gpu": nloc, "parallelism": "rows sharded x%d" % world,
                        "l2": "inputs (%.1f GB/GPU) far larger than L2" % (nloc * D * 4 / 1e9),
                        "timing": "CUDA events on the engine stream around each step, summed, max over ranks",
                        "wall_ms_per_step": wall_ms / a.steps, "F_last": Fs[-1]},
@@ -389,7 +398,7 @@ def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
             dist.barrier()
         t0 = time.perf_counter()
         eng.set_data(Xn)
-        eng.model_init(lc.BGMM)
+        eng.model_init(lc.DGMM if a.model == "dgmm" else lc.BGMM)
         zd.copy_(zh, non_blocking=True)
         torch.cuda.synchronize()
         eng.set_labels_device(zd.data_ptr(), K)

@@ -511,9 +511,12 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   }
 
   check(cudaEventRecord(ev_[0], stream_), "event");
-  if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
-  else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
-  ++launches_;
+  const bool fuse_counts = full && !sparse_ && v.N > 0;  // nz_count produces Njk in the same sweep over q
+  if (!fuse_counts) {
+    if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
+    else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
+    ++launches_;
+  }
   std::vector<double> host_njk;  // sparse mode reads the counts early
   const uint8_t* d_act = nullptr;
   if (sparse_) {
@@ -534,8 +537,9 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
       int32_t* d_cnt = (int32_t*)d_nzcnt_.p;
       long long* d_tot = (long long*)d_nzoff_.p;
       long long* d_koff = d_tot + K;
-      if (prec_ == kF32) check(dev::nz_count<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt), "nz_count");
-      else check(dev::nz_count<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt), "nz_count");
+      double* d_fused = fuse_counts ? d_njk : nullptr;
+      if (prec_ == kF32) check(dev::nz_count<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_fused), "nz_count");
+      else check(dev::nz_count<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_fused), "nz_count");
       check(dev::nz_scan(stream_, d_cnt, nb, K, d_tot), "nz_scan");
       std::vector<long long> tot(K), koff(K);
       check(cudaMemcpyAsync(tot.data(), d_tot, sizeof(long long) * K, cudaMemcpyDeviceToHost, stream_), "D2H nz totals");
@@ -563,7 +567,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
             const double span = std::max(xabs_max_ + cmax, 1e-30);
             const float scale = (float)std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(16384.0 / span)))));
             reserve(d_err_, 16);
-            ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, maxcnt, K,
+            ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, maxcnt, nnz, K,
                                   (const float*)d_cen_.p, scale, d_xs, d_S, (unsigned*)d_err_.p);
           } else {
             ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,

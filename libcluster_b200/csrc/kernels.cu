@@ -419,25 +419,38 @@ sstat_full_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
 // ---------------------------------------------------------------------------
 constexpr int kNzBlock = 2048;  // rows per counting block
 
+// Column lanes: thread (kl, rl) walks rows rl, rl+rw, ... of the block for columns kl, kl+kw, ... (no per-element
+// division).  When Njk != nullptr the same sweep also produces the per-group column sums (updateSS's Njk).
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 nz_count_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
-                const uint8_t* __restrict__ act, int32_t* __restrict__ blockcnt) {
+                const uint8_t* __restrict__ act, int kw, int32_t* __restrict__ blockcnt, double* __restrict__ Njk) {
   extern __shared__ int scnt[];
   for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
   __syncthreads();
+  const int kl = threadIdx.x % kw, rl = threadIdx.x / kw, rw = kThreads / kw;
   const int64_t r0 = (int64_t)blockIdx.x * kNzBlock;
   const int64_t r1 = (r0 + kNzBlock < N) ? r0 + kNzBlock : N;
-  const int64_t total = (r1 - r0) * K;
-  for (int64_t e = threadIdx.x; e < total; e += kThreads) {
-    const int64_t n = r0 + e / K;
-    const int k = (int)(e % K);
-    T v = q[n * ldq + k];
-    if (act != nullptr && v != (T)0) {
+  for (int k = kl; k < K; k += kw) {
+    int c = 0;
+    double acc = 0;
+    int gc = -1;
+    for (int64_t n = r0 + rl; n < r1; n += rw) {
+      T v = q[n * ldq + k];
       const int g = gid != nullptr ? gid[n] : 0;
-      if (!act[(size_t)g * K + k]) v = 0;
+      if (Njk != nullptr) {
+        if (g != gc) {
+          if (gc >= 0 && acc != 0) atomicAdd(&Njk[(size_t)gc * K + k], acc);
+          gc = g;
+          acc = 0;
+        }
+        acc += (double)v;
+      }
+      if (act != nullptr && !act[(size_t)g * K + k]) v = 0;
+      if (v != (T)0) ++c;
     }
-    if (v != (T)0) atomicAdd(&scnt[k], 1);
+    if (Njk != nullptr && gc >= 0 && acc != 0) atomicAdd(&Njk[(size_t)gc * K + k], acc);
+    if (c) atomicAdd(&scnt[k], c);
   }
   __syncthreads();
   for (int k = threadIdx.x; k < K; k += kThreads) blockcnt[(size_t)blockIdx.x * K + k] = scnt[k];
@@ -475,27 +488,27 @@ nz_scan_kernel(int32_t* __restrict__ blockcnt, int64_t nblocks, int K, long long
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 nz_fill_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
-               const uint8_t* __restrict__ act, const int32_t* __restrict__ blockoff,
+               const uint8_t* __restrict__ act, int kw, const int32_t* __restrict__ blockoff,
                const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq) {
   extern __shared__ int scnt[];
   for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
   __syncthreads();
+  const int kl = threadIdx.x % kw, rl = threadIdx.x / kw, rw = kThreads / kw;
   const int64_t r0 = (int64_t)blockIdx.x * kNzBlock;
   const int64_t r1 = (r0 + kNzBlock < N) ? r0 + kNzBlock : N;
-  const int64_t total = (r1 - r0) * K;
-  for (int64_t e = threadIdx.x; e < total; e += kThreads) {
-    const int64_t n = r0 + e / K;
-    const int k = (int)(e % K);
-    T v = q[n * ldq + k];
-    if (act != nullptr && v != (T)0) {
-      const int g = gid != nullptr ? gid[n] : 0;
-      if (!act[(size_t)g * K + k]) v = 0;
-    }
-    if (v != (T)0) {
-      const int pos = atomicAdd(&scnt[k], 1);
-      const long long o = koff[k] + blockoff[(size_t)blockIdx.x * K + k] + pos;
-      lrow[o] = (int32_t)n;
-      lq[o] = v;
+  for (int k = kl; k < K; k += kw) {
+    const long long base = koff[k] + blockoff[(size_t)blockIdx.x * K + k];
+    for (int64_t n = r0 + rl; n < r1; n += rw) {
+      T v = q[n * ldq + k];
+      if (act != nullptr && v != (T)0) {
+        const int g = gid != nullptr ? gid[n] : 0;
+        if (!act[(size_t)g * K + k]) v = 0;
+      }
+      if (v != (T)0) {
+        const int pos = atomicAdd(&scnt[k], 1);
+        lrow[base + pos] = (int32_t)n;
+        lq[base + pos] = v;
+      }
     }
   }
 }
@@ -1089,9 +1102,11 @@ cudaError_t sstat_full(cudaStream_t st, const T* X, int64_t N, int D, int64_t ld
 
 template <typename T>
 cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                     int32_t* blockcnt) {
+                     int32_t* blockcnt, double* Njk) {
   if (N <= 0) return cudaSuccess;
-  nz_count_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, blockcnt);
+  int kw = 1;
+  while (kw < K && kw < kThreads) kw <<= 1;
+  nz_count_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockcnt, Njk);
   return cudaGetLastError();
 }
 cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total) {
@@ -1102,7 +1117,9 @@ template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
                     const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq) {
   if (N <= 0) return cudaSuccess;
-  nz_fill_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, blockoff, koff,
+  int kw = 1;
+  while (kw < K && kw < kThreads) kw <<= 1;
+  nz_fill_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockoff, koff,
                                                                             lrow, lq);
   return cudaGetLastError();
 }
@@ -1281,7 +1298,7 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
                                      int64_t, int, const T*, const uint8_t*, double*, double*);                       \
   template cudaError_t colsum<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, double*);             \
   template cudaError_t nz_count<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,     \
-                                   int32_t*);                                                                         \
+                                   int32_t*, double*);                                                                \
   template cudaError_t nz_fill<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,      \
                                   const int32_t*, const long long*, int32_t*, T*);                                    \
   template cudaError_t sstat_gather_full<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \

@@ -54,7 +54,7 @@ cudaError_t colsum(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, c
 int64_t nz_blocks(int64_t N);  // row blocks used by nz_count / nz_fill
 template <typename T>
 cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                     int32_t* blockcnt /* [nz_blocks][K] */);
+                     int32_t* blockcnt /* [nz_blocks][K] */, double* Njk /* optional fused column sums */);
 cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total /* [K] */);
 template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,

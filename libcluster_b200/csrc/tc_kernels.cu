@@ -433,13 +433,13 @@ enum { SL_FULL0 = 0, SL_EMPTY0 = 2, SAB_FULL00 = 4 /* [stage][h] */, SAB_EMPTY00
 __global__ void __launch_bounds__(kScatterThreads, 1)
 sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow, const float* __restrict__ lq,
                    const long long* __restrict__ koff, const long long* __restrict__ kcnt,
-                   const float* __restrict__ cen, float scale, double* __restrict__ xs, double* __restrict__ S,
-                   unsigned* __restrict__ err) {
+                   const float* __restrict__ cen, float scale, int chunk_rows, double* __restrict__ xs,
+                   double* __restrict__ S, unsigned* __restrict__ err) {
   const int k = blockIdx.y;
   const long long cnt = kcnt[k];
-  const long long l0 = (long long)blockIdx.x * kTcScatterChunk;
+  const long long l0 = (long long)blockIdx.x * chunk_rows;
   if (l0 >= cnt) return;
-  const long long l1 = (l0 + kTcScatterChunk < cnt) ? l0 + kTcScatterChunk : cnt;
+  const long long l1 = (l0 + chunk_rows < cnt) ? l0 + chunk_rows : cnt;
   const long long base = koff[k];
   const int ntile = (int)((l1 - l0 + 127) / 128);
 
@@ -509,13 +509,16 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
         const uint32_t id = umma_idesc(128);
         if (elect_one()) {
 #pragma unroll
+          // The hi*hi products and the 2^-11 smaller cross terms go to separate accumulators: the tensor core
+          // truncates when it adds into the fp32 accumulator, and the bias of a chain of n additions (~ n/2 ulp of the
+          // running sum) must stay ~1e-7 relative for the statistics, so the big chain is kept as short as possible.
           for (int c4 = 0; c4 < 4; ++c4) {
             const uint64_t off = (uint64_t)((32 * c4) >> 4);
             const uint32_t acol = 32 * h + 8 * c4;
-            if (t == 0 && h == 0 && c4 == 0) tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, 0u);
-            else tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, 1u);
-            tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbl0 + off, id, 1u);
-            tc_mma_f16_ts(tmem_base, a_lo0 + acol, dbh0 + off, id, 1u);
+            const uint32_t first = (t == 0 && h == 0 && c4 == 0) ? 0u : 1u;
+            tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, first);
+            tc_mma_f16_ts(tmem_base + 384, a_hi0 + acol, dbl0 + off, id, first);
+            tc_mma_f16_ts(tmem_base + 384, a_lo0 + acol, dbh0 + off, id, 1u);
           }
           tc_commit(bar(SAB_EMPTY00 + 2 * st + h));
         }
@@ -608,10 +611,21 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 32 * cc)
             : "memory");
+        uint32_t r2[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
+              "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
+              "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
+              "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
+            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 384 + 32 * cc)
+            : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
-          const double v = (double)__uint_as_float(r[jj]) * inv_s2;
+          const double v = ((double)__uint_as_float(r[jj]) + (double)__uint_as_float(r2[jj])) * inv_s2;
           if (v != 0.0) atomicAdd(&Sk[(size_t)(32 * cc + jj) * kD + i], v);
         }
       }
@@ -644,15 +658,19 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
 
 
 cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
-                        const long long* kcnt, long long maxcnt, int K, const float* cen, float scale, double* xs,
-                        double* S, unsigned* err) {
+                        const long long* kcnt, long long maxcnt, long long nnz, int K, const float* cen, float scale,
+                        double* xs, double* S, unsigned* err) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  // rows folded into one fp32 TMEM accumulator before the fp64 add: fewer for small problems (more accurate, and the
+  // extra atomics are free there), kTcScatterChunk for large ones
+  const int chunk_rows = nnz <= (1LL << 20) ? 128 : kTcScatterChunk;
   cudaError_t e = cudaFuncSetAttribute(sstat_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes);
   if (e != cudaSuccess) return e;
-  const long long chunks = (maxcnt + kTcScatterChunk - 1) / kTcScatterChunk;
+  const long long chunks = (maxcnt + chunk_rows - 1) / chunk_rows;
   if (chunks > 2147483647LL || K > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)chunks, K);
-  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, cen, scale, xs, S, err);
+  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, cen, scale, chunk_rows, xs, S,
+                                                                 err);
   return cudaGetLastError();
 }
 

@@ -18,10 +18,10 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
 
 // Centred scatter over the per-cluster non-zero lists (see tc_kernels.cu); cen [K][128] is relative to the data
 // centre, scale a power of two with scale * max|x - c| <= 2^14.
-constexpr int kTcScatterChunk = 2048;  // list rows folded into one fp32 accumulator before the fp64 add
+constexpr int kTcScatterChunk = 512;  // list rows folded into the fp32 accumulators before the fp64 add (32 tensor-core additions)
 cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
-                        const long long* kcnt, long long maxcnt, int K, const float* cen, float scale, double* xs,
-                        double* S, unsigned* err);
+                        const long long* kcnt, long long maxcnt, long long nnz, int K, const float* cen, float scale,
+                        double* xs, double* S, unsigned* err);
 
 void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
 

@@ -72,8 +72,9 @@ def test_tc_overlapping_clusters_known_limit():
         eng.model_init(lc.VDP)
         eng.set_qz(q0)
         eng.vbem(maxit=3)
-        assert np.abs(eng.qZ(0) - qo).max() <= tol_q, prec
-        assert np.allclose(eng.trace()[0], m.trace()[0], rtol=tol_f), prec
+        dq = np.abs(eng.qZ(0) - qo).max()
+        dF = np.abs(eng.trace()[0] / m.trace()[0] - 1).max()
+        assert dq <= tol_q and dF <= tol_f, (prec, dq, dF)
         eng.close()
 
 
