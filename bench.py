@@ -301,18 +301,25 @@ def main():
         sampler.start()
     t0 = time.perf_counter()
     dev_ms, s_ms, e_ms, launches, Fs = 0.0, 0.0, 0.0, 0, []
+    lv = {"coarse_ms": 0.0, "lists_ms": 0.0, "refine_ms": 0.0, "finalize_ms": 0.0, "pairs": 0, "two_level_steps": 0}
     for _ in range(a.steps):
         Fs.append(eng.vbem_step())
         t = eng.step_timing()
         dev_ms += t["step_ms"]; s_ms += t["sstat_ms"]; e_ms += t["estep_ms"]; launches += t["launches"]
+        d = eng.estep_detail()
+        if d["path"] == 1:
+            lv["two_level_steps"] += 1
+            for k_ in ("coarse_ms", "lists_ms", "refine_ms", "finalize_ms", "pairs"):
+                lv[k_] += d[k_]
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
 
-    tt = torch.tensor([dev_ms, wall * 1e3, s_ms, e_ms], dtype=torch.float64, device=dev)
+    tt = torch.tensor([dev_ms, wall * 1e3, s_ms, e_ms, lv["coarse_ms"]], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms, s_ms, e_ms = [float(v) for v in tt.tolist()]
+    dev_ms, wall_ms, s_ms, e_ms, coarse_ms = [float(v) for v in tt.tolist()]
+    two_level = lv["two_level_steps"] == a.steps
     ms_per_step = dev_ms / a.steps
     value = N / (ms_per_step * 1e-3)
 
@@ -320,7 +327,15 @@ def main():
     pk = peaks()
     tc = (prec == lc.F32 and D == 128 and not diag and not os.environ.get("LCB_DISABLE_TC"))
     flops_half = (3.5 * K * D * nloc) if diag else float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
-    if e_ms >= s_ms:
+    levels = None
+    if two_level and coarse_ms >= s_ms:
+        # two-level E pass: level 1 evaluates all K*D^2 algorithmic flops of every point (one fp16 product, rigorous
+        # bound); levels 2-3 only touch the candidate pairs.  The dominant kernel is level 1.
+        kname, kms = "estep_coarse_tc128_kernel", coarse_ms / a.steps
+        traffic = None
+        levels = {k_: (lv[k_] / a.steps) for k_ in ("coarse_ms", "lists_ms", "refine_ms", "finalize_ms")}
+        levels["candidate_pairs_per_row"] = lv["pairs"] / a.steps / max(nloc, 1)
+    elif e_ms >= s_ms:
         kname, kms = ("estep_tc128_kernel" if tc else "estep_full_kernel"), e_ms / a.steps
         # measured with ncu --set full at N=2M (profiles/ncu_r01_tc_summary.md): dram read+write per point
         traffic = 756.0 * nloc if tc else None
@@ -332,10 +347,14 @@ def main():
     roofline = {"bound": "tensor", "kernel": kname, "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["_source"] + " bf16_tflops_sustained",
                 "kernel_ms": kms, "hbm_frac": (4.0 * (D + K) * nloc / (kms * 1e-3) / 1e9) / pk["hbm_gbs"],
-                "sstat_ms": s_ms / a.steps, "estep_ms": e_ms / a.steps,
-                "note": "achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
-                        "E-pass kernel; the fp16 hi/lo scheme executes 3 x 0.56 x 2 = 3.4 tensor flop per algorithmic "
-                        "flop, so tensor-pipe utilisation is higher than frac (ncu: profiles/)"}
+                "sstat_ms": s_ms / a.steps, "estep_ms": e_ms / a.steps, "estep_levels": levels,
+                "note": ("achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
+                         "level-1 kernel of the two-level E pass (one fp16 product per pair, 0.69 x 2 executed tensor "
+                         "flop per algorithmic flop incl. the centring chunk); exact logits are recomputed only for "
+                         "the candidate pairs (estep_levels)" if levels else
+                         "achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
+                         "E-pass kernel; the fp16 hi/lo scheme executes 3 x 0.56 x 2 = 3.4 tensor flop per algorithmic "
+                         "flop, so tensor-pipe utilisation is higher than frac (ncu: profiles/)")}
 
     # ---- e2e: the same step through the C ABI from HOST buffers ---------------
     e2e = None

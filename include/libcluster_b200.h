@@ -116,6 +116,12 @@ int lcb_get_trace(const lcb_engine *e, double *F, int *K);
  *   out[0] suff-stat pass, out[1] E-step pass, out[2] whole step (device),
  *   out[3] launches issued in the step. */
 int lcb_get_step_timing(lcb_engine *e, double out[4]);
+/* Break-down of the last E pass when it ran on the tensor-core tier (D = 128, LCB_F32):
+ *   out[0..3] device ms of level 1 (one-product distances + candidate marking), of the candidate lists,
+ *   of level 2 (exact logits of the candidates) and of the row soft-max;
+ *   out[4] candidate (row, cluster) pairs, out[5] path (0 dense kernel, 1 two-level, 2 two-level abandoned for
+ *   the dense kernel because too many pairs were candidates), out[6] 128-pair work items of level 2. */
+int lcb_get_estep_detail(lcb_engine *e, double out[8]);
 /* The CUDA stream all engine work is issued on (cudaStream_t as void*). */
 void *lcb_stream(lcb_engine *e);
 

@@ -47,6 +47,7 @@ SIGNATURES = {
     "lcb_trace_len": (C.c_int, [_vp]),
     "lcb_get_trace": (C.c_int, [_vp, _dp, _ip]),
     "lcb_get_step_timing": (C.c_int, [_vp, _dp]),
+    "lcb_get_estep_detail": (C.c_int, [_vp, _dp]),
     "lcb_stream": (_vp, [_vp]),
     "lcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "lcb_comm_init_nccl": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),

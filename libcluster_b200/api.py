@@ -139,6 +139,13 @@ class Engine:
         nat.check(nat.lib().lcb_get_step_timing(self._h, _dp(out)))
         return dict(sstat_ms=out[0], estep_ms=out[1], step_ms=out[2], launches=int(out[3]))
 
+    def estep_detail(self):
+        """Break-down of the last tensor-core E pass (lcb_get_estep_detail)."""
+        out = np.zeros(8)
+        nat.check(nat.lib().lcb_get_estep_detail(self._h, _dp(out)))
+        return dict(coarse_ms=out[0], lists_ms=out[1], refine_ms=out[2], finalize_ms=out[3], pairs=int(out[4]),
+                    path=int(out[5]), items=int(out[6]))
+
     @property
     def stream(self):
         return nat.lib().lcb_stream(self._h)

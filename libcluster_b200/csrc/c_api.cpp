@@ -132,6 +132,11 @@ int lcb_get_step_timing(lcb_engine* e, double out[4]) {
   e->e->get_step_timing(out);
   return LCB_OK;
 }
+int lcb_get_estep_detail(lcb_engine* e, double out[8]) {
+  if (!e || !out) return bad("null argument");
+  e->e->get_estep_detail(out);
+  return LCB_OK;
+}
 void* lcb_stream(lcb_engine* e) { return e ? (void*)e->e->stream() : nullptr; }
 
 int lcb_nccl_unique_id(char out[128]) {

@@ -94,13 +94,20 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   for (auto& e : ev_) check(cudaEventCreate(&e), "cudaEventCreate");
   const char* no_tc = std::getenv("LCB_DISABLE_TC");
   use_tc_ = !(no_tc && no_tc[0] && no_tc[0] != '0');
+  if (const char* tl = std::getenv("LCB_TC_TWO_LEVEL")) {
+    if (tl[0]) use_two_level_ = tl[0] != '0';
+  }
+  if (const char* sg = std::getenv("LCB_TC_STAGE")) {
+    if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
+    else if (std::strcmp(sg, "refine") == 0) tc_stage_ = 2;
+  }
 }
 
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_, &d_aug_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
@@ -142,6 +149,7 @@ void Engine::free_view(View& v) {
   if (v.owns_x && v.gid) cudaFree(v.gid);
   if (v.q) cudaFree(v.q);
   if (v.q2) cudaFree(v.q2);
+  if (v.xnorm) cudaFree(v.xnorm);
   v = View();
 }
 
@@ -717,13 +725,22 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   const int J = v.J, K = v.K, D = v.D;
   const size_t nblob = (size_t)K * dev::kTcBlobBytes;
   const size_t nfl = 3 * (size_t)K + (size_t)J * K;  // ascale, inv_t2, chat, lw
-  const size_t total = nblob + nfl * sizeof(float) + 16;
+  // the two-level path adds the aug blocks and its per-cluster constants behind the dense operands
+  const bool try_two = use_two_level_ && K >= 8 && K <= dev::kTcCoarseMaxK && v.N >= 1024 && (two_level_skip_ == 0 || tc_stage_ != 0);
+  if (!try_two && two_level_skip_ > 0) --two_level_skip_;
+  const size_t naug = try_two ? (size_t)((K + 3) / 4) * dev::kTcAugBlockBytes : 0;
+  const size_t ncpar = try_two ? 4 * (size_t)K : 0;
+  const size_t off_f = nblob, off_aug = (off_f + nfl * sizeof(float) + 1023) / 1024 * 1024;
+  const size_t off_cpar = off_aug + naug, total = off_cpar + ncpar * sizeof(float) + 16;
   unsigned char* h = (unsigned char*)pinned(total);
-  float* f = reinterpret_cast<float*>(h + nblob);
+  float* f = reinterpret_cast<float*>(h + off_f);
   float* h_as = f;
   float* h_it2 = h_as + K;
   float* h_chat = h_it2 + K;
   float* h_lw = h_chat + K;
+  unsigned char* h_aug = h + off_aug;
+  float* h_cpar = reinterpret_cast<float*>(h + off_cpar);
+  if (naug) std::memset(h_aug, 0, naug);
   std::vector<double> cc(K);
   double cbar = 0;
   for (int k = 0; k < K; ++k) {
@@ -731,16 +748,21 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     cbar += cc[k];
   }
   cbar /= K;
-#pragma omp parallel for schedule(dynamic) if (K >= 8)
+  // level-1 operand scale: s_g max|x| <= 2^8 keeps fp16(s_g x) far from saturation and its small entries normal
+  const double xspan = std::max(xabs_max_, 1e-30);
+  const double sg = std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(256.0 / xspan)))));
+  std::vector<double> vaug(try_two ? (size_t)K * D : 0), tau(K), rfro(K);
+  double vmax = 0;
+#pragma omp parallel for schedule(dynamic) reduction(max : vmax) if (K >= 8)
   for (int k = 0; k < K; ++k) {
     std::vector<double> R;
     clusters[k].whitener(R);
     // a = s (x - m): s maps the widest posterior standard deviation to ~32
     const std::vector<double> cov = clusters[k].cov();
-    double vmax = 0, rmax = 0;
-    for (int d = 0; d < D; ++d) vmax = std::max(vmax, cov[(size_t)d * D + d]);
+    double cvmax = 0, rmax = 0;
+    for (int d = 0; d < D; ++d) cvmax = std::max(cvmax, cov[(size_t)d * D + d]);
     for (size_t i = 0; i < R.size(); ++i) rmax = std::max(rmax, std::fabs(R[i]));
-    int es_ = (int)std::lround(std::log2(32.0 / std::sqrt(std::max(vmax, 1e-300))));
+    int es_ = (int)std::lround(std::log2(32.0 / std::sqrt(std::max(cvmax, 1e-300))));
     es_ = std::min(60, std::max(-60, es_));
     const double s = std::ldexp(1.0, es_);
     // b = (t / s) R: t puts the largest entry of R / s near 2^8
@@ -754,15 +776,54 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     h_as[k] = (float)s;
     h_it2[k] = (float)(1.0 / (t * t));
     h_chat[k] = (float)(cc[k] - cbar);
+    if (try_two) {
+      // accumulator of level 1 = s_g tau (R x - R m): the centring term and |R|_F for the error bound
+      tau[k] = t / s;
+      double fro = 0;
+      for (int i = 0; i < D; ++i) {
+        double acc = 0;
+        for (int d = 0; d <= i; ++d) {
+          const double r = R[(size_t)i * D + d];
+          acc += r * rel[d];
+          fro += r * r;
+        }
+        const double val = sg * tau[k] * acc;
+        vaug[(size_t)k * D + i] = val;
+        vmax = std::max(vmax, std::fabs(val));
+      }
+      rfro[k] = std::sqrt(fro);
+    }
   }
   for (int j = 0; j < J; ++j) {
     const std::vector<double>& e = weights[j].Elogweight();
     for (int k = 0; k < K; ++k) h_lw[(size_t)j * K + k] = (float)e[k];
   }
+  bool two_ok = try_two;
+  int aug_exp = 0;
+  if (try_two) {
+    // A slot of the aug chunk = 2^P, B slots = -v / 2^P split three ways: |v| / 2^P <= 2^14
+    aug_exp = vmax > 16384.0 ? (int)std::ceil(std::log2(vmax / 16384.0)) : 0;
+    if (aug_exp > 15 || !(xabs_max_ > 0) || !std::isfinite(vmax)) two_ok = false;
+  }
+  if (two_ok) {
+    const double p2 = std::ldexp(1.0, aug_exp);
+    const double eps = 1.0625 * std::ldexp(1.0, -10);  // two fp16 roundings + fp32 accumulation of 144 terms
+    for (int k = 0; k < K; ++k) {
+      std::vector<double> w(D);
+      for (int i = 0; i < D; ++i) w[i] = -vaug[(size_t)k * D + i] / p2;
+      const double res = dev::tc_pack_aug(w.data(), k, h_aug);  // in accumulator units / 2^P
+      const double unit = sg * tau[k];
+      h_cpar[k] = (float)(1.0 / (unit * unit));
+      h_cpar[(size_t)K + k] = (float)(eps * rfro[k] * (1.0 + 1e-6));
+      h_cpar[2 * (size_t)K + k] =
+          (float)((eps * rfro[k] * xabs_max_ * std::ldexp(1.0, -12) + std::sqrt((double)D) * res * p2 / unit) * (1.0 + 1e-6));
+      h_cpar[3 * (size_t)K + k] = h_chat[k];
+    }
+  }
   reserve(d_tc_, total);
   check(cudaMemcpyAsync(d_tc_.p, h, total, cudaMemcpyHostToDevice, stream_), "H2D tc params");
   const uint8_t* d_blob = (const uint8_t*)d_tc_.p;
-  const float* df = reinterpret_cast<const float*>(d_blob + nblob);
+  const float* df = reinterpret_cast<const float*>(d_blob + off_f);
   const float* d_as = df;
   const float* d_it2 = d_as + K;
   const float* d_chat = d_it2 + K;
@@ -774,16 +835,112 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   unsigned* d_err = (unsigned*)(d_fz + 1);
   check(cudaMemsetAsync(d_fz, 0, sizeof(double) * 2, stream_), "memset");
   check(cudaEventRecord(ev_[2], stream_), "event");
-  check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw,
-                         d_act, (float*)v.q, v.ldq, d_fz, d_err),
-        "estep_tc128 launch");
-  ++launches_;
+  bool done = false;
+  for (double& x : estep_detail_) x = 0;
+  if (two_ok)
+    done = ephase_two_level(v, K, d_blob, d_as, d_it2, d_chat, d_lw, d_act, d_blob + off_aug, naug,
+                            reinterpret_cast<const float*>(d_blob + off_cpar), (float)sg, aug_exp, d_fz, d_err);
+  if (!done) {
+    check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw,
+                           d_act, (float*)v.q, v.ldq, d_fz, d_err),
+          "estep_tc128 launch");
+    ++launches_;
+  }
   check(cudaEventRecord(ev_[3], stream_), "event");
   allreduce(d_fz, 1);
   double out[2] = {0, 0};
   check(cudaMemcpyAsync(out, d_fz, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream_), "D2H Fz");
   sync();
+  if (estep_detail_[5] == 1) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_[4], ev_[5]);
+    estep_detail_[0] = ms;
+    cudaEventElapsedTime(&ms, ev_[5], ev_[6]);
+    estep_detail_[1] = ms;
+    cudaEventElapsedTime(&ms, ev_[6], ev_[7]);
+    estep_detail_[2] = ms;
+    cudaEventElapsedTime(&ms, ev_[7], ev_[8]);
+    estep_detail_[3] = ms;
+  }
   return -(out[0] + (double)v_ntot_ * cbar);
+}
+
+// Two-level E step on the tensor cores.  Returns false when the dense kernel has to run
+// instead (too many candidate pairs for the two levels to pay); q then holds scratch values.
+bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float* d_as, const float* d_it2,
+                              const float* d_chat, const float* d_lw, const uint8_t* d_act, const unsigned char* d_aug,
+                              size_t aug_bytes, const float* d_cpar, float sg, int aug_exp, double* d_fz,
+                              unsigned* d_err) {
+  (void)aug_bytes;
+  const float kMargin = 24.f;  // pairs that cannot reach e^-24 of the row's best get q = 0
+  if (v.xnorm == nullptr) {
+    dev_alloc((void**)&v.xnorm, sizeof(float) * (size_t)std::max<int64_t>(v.N, 1));
+    check(dev::row_norm128(stream_, sms_, (const float*)v.X, v.N, v.xnorm), "row_norm128");
+    ++launches_;
+  }
+  float* q = (float*)v.q;
+  check(cudaEventRecord(ev_[4], stream_), "event");
+  check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
+                                d_act, sg, aug_exp, kMargin, q, v.ldq, d_err),
+        "estep_coarse_tc128 launch");
+  ++launches_;
+  check(cudaEventRecord(ev_[5], stream_), "event");
+  estep_detail_[5] = 1;
+  if (tc_stage_ == 1) {
+    for (int i = 6; i <= 8; ++i) check(cudaEventRecord(ev_[i], stream_), "event");
+    return true;
+  }
+  // candidate pairs as per-cluster row lists
+  const int64_t nb = dev::nz_blocks(v.N);
+  reserve(d_nzcnt_, sizeof(int32_t) * (size_t)nb * K);
+  reserve(d_nzoff_, sizeof(long long) * (size_t)(2 * K + 2) + sizeof(int32_t) * (size_t)(K + 2));
+  int32_t* d_cnt = (int32_t*)d_nzcnt_.p;
+  long long* d_tot = (long long*)d_nzoff_.p;
+  long long* d_koff = d_tot + K;
+  int32_t* d_itoff = (int32_t*)(d_koff + K + 2);
+  check(dev::nz_count<float>(stream_, q, v.ldq, v.N, K, nullptr, nullptr, d_cnt, nullptr, dev::kNzNotNegInf), "nz_count");
+  check(dev::nz_scan(stream_, d_cnt, nb, K, d_tot), "nz_scan");
+  launches_ += 2;
+  std::vector<long long> tot(K), koff(K);
+  check(cudaMemcpyAsync(tot.data(), d_tot, sizeof(long long) * K, cudaMemcpyDeviceToHost, stream_), "D2H candidate totals");
+  sync();
+  std::vector<int32_t> itoff(K + 1);
+  long long npairs = 0, nitems = 0;
+  for (int k = 0; k < K; ++k) {
+    koff[k] = npairs;
+    itoff[k] = (int32_t)nitems;
+    npairs += tot[k];
+    nitems += (tot[k] + 127) / 128;
+  }
+  itoff[K] = (int32_t)nitems;
+  estep_detail_[4] = (double)npairs;
+  estep_detail_[6] = (double)nitems;
+  // each candidate costs about three products plus a gather; level 1 cost one product for all K
+  if (tc_stage_ == 0 && ((double)npairs > 0.4 * (double)K * (double)v.N || nitems > 2000000000LL)) {
+    estep_detail_[5] = 2;
+    two_level_skip_ = 8;
+    return false;
+  }
+  check(cudaMemcpyAsync(d_koff, koff.data(), sizeof(long long) * K, cudaMemcpyHostToDevice, stream_), "H2D koff");
+  check(cudaMemcpyAsync(d_itoff, itoff.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, stream_), "H2D itoff");
+  reserve(d_list_, (size_t)std::max<long long>(npairs, 1) * 4 + 256);
+  int32_t* lrow = (int32_t*)d_list_.p;
+  check(dev::nz_fill<float>(stream_, q, v.ldq, v.N, K, nullptr, nullptr, d_cnt, d_koff, lrow, nullptr, dev::kNzNotNegInf), "nz_fill");
+  ++launches_;
+  check(cudaEventRecord(ev_[6], stream_), "event");
+  check(dev::estep_tc128_list(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw, lrow,
+                              d_koff, d_tot, d_itoff, nitems, q, v.ldq, d_err),
+        "estep_tc128_list launch");
+  ++launches_;
+  check(cudaEventRecord(ev_[7], stream_), "event");
+  if (tc_stage_ == 2) {
+    check(cudaEventRecord(ev_[8], stream_), "event");
+    return true;
+  }
+  check(dev::estep_finalize(stream_, sms_, q, v.ldq, v.N, K, d_fz), "estep_finalize");
+  ++launches_;
+  check(cudaEventRecord(ev_[8], stream_), "event");
+  return true;
 }
 
 void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
@@ -1198,6 +1355,10 @@ void Engine::vbem_step(double* F) {
   step_launches_ = launches_ - l0;
   last_F_ = f;
   if (F) *F = f;
+}
+
+void Engine::get_estep_detail(double out[8]) const {
+  for (int i = 0; i < 8; ++i) out[i] = estep_detail_[i];
 }
 
 void Engine::get_step_timing(double out[4]) {

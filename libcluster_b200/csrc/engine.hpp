@@ -31,6 +31,7 @@ struct View {
   int64_t ldq = 0;
   int K = 0;
   bool owns_x = false;
+  float* xnorm = nullptr;  // |x_n| of every row (fp32 engine, D == 128; filled on first use by the two-level E step)
 };
 
 struct DeviceBuf {
@@ -63,6 +64,7 @@ class Engine {
   const std::vector<double>& trace_F() const { return trace_F_; }
   const std::vector<int>& trace_K() const { return trace_K_; }
   void get_step_timing(double out[4]);
+  void get_estep_detail(double out[8]) const;
   cudaStream_t stream() const { return stream_; }
 
   void comm_init_nccl(const char id[128], int rank, int world);
@@ -92,6 +94,9 @@ class Engine {
   double ephase(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters, int mode,
                 std::vector<double>* H);
   double ephase_tc(View& v, const std::vector<WeightPost>& weights, const std::vector<ClusterPost>& clusters);
+  bool ephase_two_level(View& v, int K, const uint8_t* d_blob, const float* d_as, const float* d_it2,
+                        const float* d_chat, const float* d_lw, const uint8_t* d_act, const unsigned char* d_aug,
+                        size_t aug_bytes, const float* d_cpar, float sg, int aug_exp, double* d_fz, unsigned* d_err);
   void group_counts(View& v, std::vector<double>& Njk);
   bool prune(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters);
   bool split_gr(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
@@ -104,6 +109,12 @@ class Engine {
 
   int device_, prec_, sms_;
   bool use_tc_ = true;  // tcgen05 tier of the E step (LCB_DISABLE_TC=1 forces the SIMT tier)
+  // Two-level E step (one-product distances for all pairs, exact logits for the candidates only).
+  // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
+  bool use_two_level_ = true;
+  int tc_stage_ = 0;            // 0 full, 1 stop after level 1, 2 stop after level 2
+  int two_level_skip_ = 0;      // iterations left before the two-level path is tried again after it did not pay
+  double estep_detail_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t stream_ = nullptr;
   View main_;
   std::vector<int64_t> Nj_;       // local rows per group
@@ -126,13 +137,13 @@ class Engine {
   bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
 
   // device scratch
-  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_, d_err_;
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_, d_err_, d_aug_;
   std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;
 
   // timing of the last step
-  cudaEvent_t ev_[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double t_s_ = 0, t_e_ = 0, t_all_ = 0;
   long launches_ = 0, step_launches_ = 0;
 

@@ -424,7 +424,8 @@ constexpr int kNzBlock = 2048;  // rows per counting block
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 nz_count_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
-                const uint8_t* __restrict__ act, int kw, int32_t* __restrict__ blockcnt, double* __restrict__ Njk) {
+                const uint8_t* __restrict__ act, int kw, int32_t* __restrict__ blockcnt, double* __restrict__ Njk,
+                int pred) {
   extern __shared__ int scnt[];
   for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
   __syncthreads();
@@ -445,6 +446,10 @@ nz_count_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const in
           acc = 0;
         }
         acc += (double)v;
+      }
+      if (pred == kNzNotNegInf) {
+        if (v != -(T)INFINITY) ++c;
+        continue;
       }
       if (act != nullptr && !act[(size_t)g * K + k]) v = 0;
       if (v != (T)0) ++c;
@@ -489,7 +494,7 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 nz_fill_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
                const uint8_t* __restrict__ act, int kw, const int32_t* __restrict__ blockoff,
-               const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq) {
+               const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq, int pred) {
   extern __shared__ int scnt[];
   for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
   __syncthreads();
@@ -500,6 +505,13 @@ nz_fill_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int
     const long long base = koff[k] + blockoff[(size_t)blockIdx.x * K + k];
     for (int64_t n = r0 + rl; n < r1; n += rw) {
       T v = q[n * ldq + k];
+      if (pred == kNzNotNegInf) {
+        if (v != -(T)INFINITY) {
+          const int pos = atomicAdd(&scnt[k], 1);
+          lrow[base + pos] = (int32_t)n;
+        }
+        continue;
+      }
       if (act != nullptr && v != (T)0) {
         const int g = gid != nullptr ? gid[n] : 0;
         if (!act[(size_t)g * K + k]) v = 0;
@@ -1102,11 +1114,12 @@ cudaError_t sstat_full(cudaStream_t st, const T* X, int64_t N, int D, int64_t ld
 
 template <typename T>
 cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                     int32_t* blockcnt, double* Njk) {
+                     int32_t* blockcnt, double* Njk, int pred) {
   if (N <= 0) return cudaSuccess;
   int kw = 1;
   while (kw < K && kw < kThreads) kw <<= 1;
-  nz_count_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockcnt, Njk);
+  nz_count_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockcnt, Njk,
+                                                                             pred);
   return cudaGetLastError();
 }
 cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total) {
@@ -1115,12 +1128,12 @@ cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, 
 }
 template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq) {
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred) {
   if (N <= 0) return cudaSuccess;
   int kw = 1;
   while (kw < K && kw < kThreads) kw <<= 1;
   nz_fill_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockoff, koff,
-                                                                            lrow, lq);
+                                                                            lrow, lq, pred);
   return cudaGetLastError();
 }
 int64_t nz_blocks(int64_t N) { return (N + kNzBlock - 1) / kNzBlock; }
@@ -1298,9 +1311,9 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
                                      int64_t, int, const T*, const uint8_t*, double*, double*);                       \
   template cudaError_t colsum<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, double*);             \
   template cudaError_t nz_count<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,     \
-                                   int32_t*, double*);                                                                \
+                                   int32_t*, double*, int);                                                           \
   template cudaError_t nz_fill<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,      \
-                                  const int32_t*, const long long*, int32_t*, T*);                                    \
+                                  const int32_t*, const long long*, int32_t*, T*, int);                               \
   template cudaError_t sstat_gather_full<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \
                                             const long long*, const long long*, long long, int, const T*, double*,   \
                                             double*);                                                                 \

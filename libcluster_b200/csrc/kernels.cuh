@@ -52,13 +52,17 @@ cudaError_t colsum(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, c
 // Non-zero responsibilities as per-cluster (row, q) lists and the full-covariance
 // statistics over those lists (work proportional to nnz(q), not N*K).
 int64_t nz_blocks(int64_t N);  // row blocks used by nz_count / nz_fill
+// which entries go on the lists: q != 0 (responsibilities, after the sparse mask) or q != -inf (the candidate
+// marking left by estep_coarse_tc128; the mask and Njk are ignored and lq may be NULL)
+enum NzPred { kNzNonZero = 0, kNzNotNegInf = 1 };
 template <typename T>
 cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                     int32_t* blockcnt /* [nz_blocks][K] */, double* Njk /* optional fused column sums */);
+                     int32_t* blockcnt /* [nz_blocks][K] */, double* Njk /* optional fused column sums */,
+                     int pred = kNzNonZero);
 cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total /* [K] */);
 template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq);
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred = kNzNonZero);
 template <typename T>
 cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
                               const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,

@@ -27,6 +27,8 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
 
 #include "kernels.cuh"
@@ -188,12 +190,41 @@ __device__ __forceinline__ float2 centre_scale2(float2 x, float2 mh, float2 s2, 
   return *reinterpret_cast<float2*>(&A);
 }
 
+// One unit of work of the list mode: 128 consecutive entries of one cluster's candidate list.
+struct ListItem {
+  int k;          // cluster
+  int count;      // valid entries (<= 128)
+  long long base; // first entry in lrow
+};
+__device__ __forceinline__ ListItem list_item(int64_t it, int K, const int32_t* __restrict__ itoff,
+                                              const long long* __restrict__ koff, const long long* __restrict__ kcnt) {
+  int lo = 0, hi = K - 1;  // last k with itoff[k] <= it
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int64_t)__ldg(itoff + mid) <= it) lo = mid;
+    else hi = mid - 1;
+  }
+  ListItem r;
+  r.k = lo;
+  const long long first = (long long)(it - __ldg(itoff + lo)) * kTM;
+  const long long left = __ldg(kcnt + lo) - first;
+  r.count = (int)(left < kTM ? left : kTM);
+  r.base = __ldg(koff + lo) + first;
+  return r;
+}
+
+// kList == false: every 128-row tile of X against all K clusters, row soft-max in the epilogue (q, log Z).
+// kList == true : the work items are 128-entry chunks of per-cluster row lists (lrow; item -> cluster through
+//                 itoff); the kernel writes the exact logit of every (row, cluster) pair into q[row][cluster]
+//                 and leaves the soft-max to estep_finalize_kernel.
+template <bool kList>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __restrict__ gid, int K,
                    const uint8_t* __restrict__ blob, const float* __restrict__ ascale,
                    const float* __restrict__ inv_t2, const float* __restrict__ chat, const float* __restrict__ lw,
                    const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq, double* __restrict__ Fz,
-                   unsigned* __restrict__ err) {
+                   unsigned* __restrict__ err, const int32_t* __restrict__ lrow, const long long* __restrict__ koff,
+                   const long long* __restrict__ kcnt, const int32_t* __restrict__ itoff, int64_t nitems) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -202,7 +233,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ntiles = (N + kTM - 1) / kTM;
+  const int64_t ntiles = kList ? nitems : (N + kTM - 1) / kTM;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -239,7 +270,12 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     if (warp == 0 && lane == 0) {
       uint32_t cnt = 0;
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int k = 0; k < K; ++k, ++cnt) {
+        int k0 = 0, k1 = K;
+        if constexpr (kList) {
+          k0 = list_item(tile, K, itoff, koff, kcnt).k;
+          k1 = k0 + 1;
+        }
+        for (int k = k0; k < k1; ++k, ++cnt) {
           const uint32_t st = cnt % kStages, ph = (cnt / kStages) & 1;
           mbar_wait(bar(BB_EMPTY0 + st), ph ^ 1, err);
           mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
@@ -253,7 +289,8 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     if (warp == 1) {
       uint32_t cnt = 0;  // clusters processed so far (all rings advance once per cluster)
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int k = 0; k < K; ++k, ++cnt) {
+        const int nk = kList ? 1 : K;
+        for (int k = 0; k < nk; ++k, ++cnt) {
           const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
           const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
           mbar_wait(bar(BT_EMPTY0 + st), ph ^ 1, err);
@@ -298,14 +335,22 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     double fz = 0;
     uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t n = tile * kTM + ew * 32 + lane;
-      const bool valid = n < N;
+      int64_t n = tile * kTM + ew * 32 + lane;
+      bool valid = n < N;
+      int k0 = 0, k1 = K;
+      if constexpr (kList) {
+        const ListItem item = list_item(tile, K, itoff, koff, kcnt);
+        k0 = item.k;
+        k1 = k0 + 1;
+        valid = ew * 32 + lane < item.count;
+        n = valid ? (int64_t)__ldg(lrow + item.base + ew * 32 + lane) : 0;
+      }
       const int g = (gid != nullptr && valid) ? gid[n] : 0;
       const float* lwg = lw + (size_t)g * K;
       const uint8_t* actg = act != nullptr ? act + (size_t)g * K : nullptr;
       float* qrow = q + (valid ? n : 0) * ldq;
       float mx = -INFINITY, se = 0.f;  // running max / sum of exp for the row soft-max
-      for (int k = 0; k < K; ++k, ++cnt) {
+      for (int k = k0; k < k1; ++k, ++cnt) {
         const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
         mbar_wait(bar(BT_FULL0 + st), ph, err);
         tc_fence_after();
@@ -318,6 +363,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         float l = chat[k] + lwg[k] - 0.5f * inv_t2[k] * s;
         if (actg != nullptr && !actg[k]) l = -INFINITY;
         if (valid) qrow[k] = l;
+        if constexpr (kList) continue;
         if (l > mx) {
           se = se * expf(mx - l) + 1.f;
           mx = l;
@@ -325,7 +371,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
           se += expf(l - mx);
         }
       }
-      if (valid) {
+      if (!kList && valid) {
         // q = exp(logit - logZ) from the logits parked in the q row (L2-resident)
         const float lz = logf(se) + mx;
         float4* q4 = reinterpret_cast<float4*>(qrow);
@@ -339,8 +385,10 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         fz += (double)lz;
       }
     }
-    for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
-    if (lane == 0) atomicAdd(Fz, fz);
+    if constexpr (!kList) {
+      for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
+      if (lane == 0) atomicAdd(Fz, fz);
+    }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     // ------------------------------------------------------ operand builders --
@@ -349,7 +397,14 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     const int row = 32 * quad + lane;
     uint32_t cnt = 0;
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int64_t n = tile * kTM + row;
+      int64_t n = tile * kTM + row;
+      int k0 = 0, k1 = K;
+      if constexpr (kList) {
+        const ListItem item = list_item(tile, K, itoff, koff, kcnt);
+        k0 = item.k;
+        k1 = k0 + 1;
+        n = row < item.count ? (int64_t)__ldg(lrow + item.base + row) : N;
+      }
       float4 x[16];
       if (n < N) {
         const float4* src = reinterpret_cast<const float4*>(X + n * kD + 64 * kb);
@@ -359,7 +414,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      for (int k = 0; k < K; ++k, ++cnt) {
+      for (int k = k0; k < k1; ++k, ++cnt) {
         const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
         const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
         const float sc = ascale[k];
@@ -639,6 +694,489 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
   }
 }
 
+
+// ===========================================================================
+// Two-level E step, level 1: estep_coarse_tc128_kernel (D == 128, fp32 engine).
+//
+// Every (row, cluster) distance is first computed with ONE fp16 product
+// (hi * hi, no per-cluster operand build): A = fp16(s_g x) is converted once per
+// 128-row tile and serves all K clusters, B_k is the hi half of the dense kernel's
+// blob, and the centring -R_k m_k enters the accumulator through one extra K chunk
+// (A = 2^P in three slots, B = the fp16 hi/mid/lo split of -s_g tau_k (R_k m_k)_i / 2^P).
+// The result has a rigorous error bound:
+//     | d~ - d | <= E_nk = Ek[k] * |x_n| + Ea[k],     d = | R_k (x_n - m_k) |
+// so each logit is bracketed, LB <= logit <= UB.  A pair (n, k) is a *candidate*
+// iff UB_nk >= max_j LB_nj - margin; only candidates can have q > e^-margin.  The
+// kernel leaves UB (candidates) or -inf (others) in q; level 2 (the list mode of
+// estep_tc128_kernel) recomputes the candidates at fp32-equivalent accuracy and
+// estep_finalize_kernel forms q and log Z.
+//
+// One persistent CTA per SM works on groups of kCT = 3 tiles (384 rows) so that a
+// cluster's operand, streamed from L2 by the TMA engine, is used by three MMAs
+// chains: 16 warps =
+//   warp 0      producer: cp.async.bulk of B_k (24 KB, 3-stage ring) and of the
+//               aug blocks (16 KB per 4 clusters, 2-stage ring)
+//   warp 1      MMA issue: per (cluster, tile) 1 aug + 8 triangular chunk MMAs
+//   warp 2      TMEM allocation
+//   warps 4-7   stagers: X -> fp16 staging in shared memory during the previous
+//               group, staging -> TMEM A at the group boundary; they also turn the
+//               parked UB rows of the finished group into the candidate marking
+//   warps 8-15  two epilogue groups, one per accumulator: tcgen05.ld the 128
+//               accumulator columns, release the accumulator, sum of squares,
+//               bounds, park UB in the q row
+// TMEM: accumulators [0,128) [128,256); A of tile slot s at 256 + 72 s (64 columns
+// of data + 8 of the aug chunk).
+// ===========================================================================
+constexpr int kCT = 3;
+constexpr int kCRows = kCT * kTM;                              // 384 rows per group
+constexpr int kCStages = 3;
+constexpr uint32_t kCBStage = 24576;                           // hi block 0 (16 KB) + hi block 1 (8 KB)
+constexpr uint32_t kCOffAug = kCStages * kCBStage;             // 73728
+constexpr uint32_t kCOffStageA = kCOffAug + 2 * kTcAugBlockBytes;  // 106496
+constexpr uint32_t kCStageA = 32768;                           // one tile as fp16 [128][128], 16-byte chunks XOR (row & 15)
+constexpr uint32_t kCOffPar = kCOffStageA + kCT * kCStageA;    // 204800: per-cluster floats [4][256]
+constexpr uint32_t kCOffLb = kCOffPar + 4 * 256 * 4;           // 208896: [2 parities][2 groups][384] lower-bound maxima
+constexpr uint32_t kCOffBar = kCOffLb + 2 * 2 * kCRows * 4;    // 215040
+constexpr uint32_t kCSmemBytes = kCOffBar + 512 + 1024;
+constexpr uint32_t kCAcol = 72;                                // TMEM columns of one A slot
+enum {
+  CB_FULL0 = 0, CB_EMPTY0 = 3, CG_FULL0 = 6, CG_EMPTY0 = 8, CA_READY0 = 10, CA_FREE0 = 13, CT_FULL0 = 16, CT_EMPTY0 = 18,
+  CL_FULL0 = 20, CL_FREE0 = 22, C_COUNT = 24
+};
+
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+      "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+      "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]),
+        "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]),
+        "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]),
+        "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]),
+        "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+// sum of squares of 64 fp32 register values with packed FMAs, four independent chains
+__device__ __forceinline__ float sumsq64(const uint32_t* r) {
+  unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int i = 0; i < 64; i += 8) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      unsigned long long p;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "r"(r[i + 2 * c]), "r"(r[i + 2 * c + 1]));
+      asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc[c]) : "l"(p));
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t a, b;
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(acc[c]));
+    s += __uint_as_float(a) + __uint_as_float(b);
+  }
+  return s;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreadsTc, 1)
+estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__ xnorm, int64_t N,
+                          const int32_t* __restrict__ gid, int K, const uint8_t* __restrict__ blob,
+                          const uint8_t* __restrict__ augblob, const float* __restrict__ cpar /* [4][K] */,
+                          const float* __restrict__ lw, const uint8_t* __restrict__ act, float sg, uint32_t aug01,
+                          uint32_t aug2, float margin, float* __restrict__ q, int64_t ldq, unsigned* __restrict__ err) {
+  extern __shared__ unsigned char smem_dyn[];
+  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
+  const uint32_t sBar = sbase + kCOffBar;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT);
+  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
+  float* spar = reinterpret_cast<float*>(sgen + kCOffPar);  // [0] cinv2, [1] Ek, [2] Ea, [3] chat; stride 256
+  float* slb = reinterpret_cast<float*>(sgen + kCOffLb);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ngroups = (N + kCRows - 1) / kCRows;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kCStages; ++i) {
+      mbar_init(bar(CB_FULL0 + i), 1);
+      mbar_init(bar(CB_EMPTY0 + i), 1);
+      mbar_init(bar(CA_READY0 + i), 4);  // 4 stager warps (lane quadrants)
+      mbar_init(bar(CA_FREE0 + i), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar(CG_FULL0 + i), 1);
+      mbar_init(bar(CG_EMPTY0 + i), 1);
+      mbar_init(bar(CT_FULL0 + i), 1);
+      mbar_init(bar(CT_EMPTY0 + i), 4);  // 4 warps of the epilogue group
+      mbar_init(bar(CL_FULL0 + i), 8);   // 8 epilogue warps
+      mbar_init(bar(CL_FREE0 + i), 4);   // 4 stager warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 4 * 256; i += kThreadsTc) {
+    const int a = i >> 8, k = i & 255;
+    spar[i] = k < K ? cpar[(size_t)a * K + k] : 0.f;
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32((const void*)tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0 && lane == 0) {
+      // ---------------------------------------------------------- producer --
+      uint32_t bcnt = 0, acnt = 0;
+      for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
+        for (int k = 0; k < K; ++k, ++bcnt) {
+          if ((k & 3) == 0) {
+            const uint32_t as = acnt & 1, aph = (acnt >> 1) & 1;
+            mbar_wait(bar(CG_EMPTY0 + as), aph ^ 1, err);
+            mbar_expect_tx(bar(CG_FULL0 + as), kTcAugBlockBytes);
+            bulk_g2s(sbase + kCOffAug + as * kTcAugBlockBytes, augblob + (size_t)(k >> 2) * kTcAugBlockBytes,
+                     kTcAugBlockBytes, bar(CG_FULL0 + as));
+            ++acnt;
+          }
+          const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
+          mbar_wait(bar(CB_EMPTY0 + bs), bph ^ 1, err);
+          mbar_expect_tx(bar(CB_FULL0 + bs), kCBStage);
+          const uint8_t* src = blob + (size_t)k * kBBlob;
+          bulk_g2s(sbase + bs * kCBStage, src, 16384u, bar(CB_FULL0 + bs));                  // hi, dims 0..63
+          bulk_g2s(sbase + bs * kCBStage + 16384u, src + 32768u, 8192u, bar(CB_FULL0 + bs));  // hi, dims 64..127
+        }
+      }
+    }
+    if (warp == 1) {
+      // -------------------------------------------------------- MMA issuer --
+      uint32_t bcnt = 0, acnt = 0, icnt = 0, gcnt = 0, as = 0;
+      for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
+        for (int k = 0; k < K; ++k, ++bcnt) {
+          const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
+          if ((k & 3) == 0) {
+            as = acnt & 1;
+            mbar_wait(bar(CG_FULL0 + as), (acnt >> 1) & 1, err);
+            ++acnt;
+          }
+          mbar_wait(bar(CB_FULL0 + bs), bph, err);
+          const uint32_t sBk = sbase + bs * kCBStage;
+          const uint64_t db0 = umma_desc(sBk), db1 = umma_desc(sBk + 16384u);
+          const uint64_t dbg = umma_desc(sbase + kCOffAug + as * kTcAugBlockBytes) + (uint64_t)(2 * (k & 3));
+          const bool last_k = k == K - 1;
+#pragma unroll 1
+          for (int s = 0; s < kCT; ++s, ++icnt) {
+            const uint32_t a = icnt & 1, ph = (icnt >> 1) & 1;
+            if (k == 0) mbar_wait(bar(CA_READY0 + s), gcnt & 1, err);
+            mbar_wait(bar(CT_EMPTY0 + a), ph ^ 1, err);
+            tc_fence_after();
+            const uint32_t d0 = tmem_base + 128u * a;
+            const uint32_t a0 = tmem_base + 256u + kCAcol * (uint32_t)s;
+            if (elect_one()) {
+              // accumulator = -s_g tau_k R_k m_k (aug chunk), then the 8 triangular chunks
+              tc_mma_f16_ts(d0, a0 + 64u, dbg, umma_idesc(128), 0u);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const int kb = c >> 2, c4 = c & 3;
+                const uint64_t off = (uint64_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
+                tc_mma_f16_ts(d0 + 16 * c, a0 + 8 * c, (kb ? db1 : db0) + off, umma_idesc(128 - 16 * c), 1u);
+              }
+              tc_commit(bar(CT_FULL0 + a));
+              if (last_k) tc_commit(bar(CA_FREE0 + s));
+            }
+            __syncwarp();
+          }
+          const bool aug_done = (k & 3) == 3 || last_k;
+          if (elect_one()) {
+            tc_commit(bar(CB_EMPTY0 + bs));
+            if (aug_done) tc_commit(bar(CG_EMPTY0 + as));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    // --------------------------------------------------------------- stagers --
+    const int sw = warp - 4;  // == lane quadrant of the TMEM rows this warp may touch
+    // X rows of group gi -> fp16(s_g x) in the staging buffers; a warp converts two rows per step
+    auto stage_group = [&](int64_t gi) {
+      for (int t = 0; t < kCT; ++t) {
+        const int64_t n0 = gi * kCRows + (int64_t)t * kTM;
+        unsigned char* dstT = sgen + kCOffStageA + (uint32_t)t * kCStageA;
+#pragma unroll 1
+        for (int it0 = 0; it0 < 16; it0 += 4) {
+          float4 v[4][2];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
+            const int64_t n = n0 + r;
+            if (n < N) {
+              const float4* src = reinterpret_cast<const float4*>(X + n * kD + 8 * (lane & 15));
+              v[u][0] = __ldg(src);
+              v[u][1] = __ldg(src + 1);
+            } else {
+              v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
+            uint4 w;
+            w.x = pack_f16x2_sat(v[u][0].x * sg, v[u][0].y * sg);
+            w.y = pack_f16x2_sat(v[u][0].z * sg, v[u][0].w * sg);
+            w.z = pack_f16x2_sat(v[u][1].x * sg, v[u][1].y * sg);
+            w.w = pack_f16x2_sat(v[u][1].z * sg, v[u][1].w * sg);
+            *reinterpret_cast<uint4*>(dstT + r * 256 + (((lane & 15) ^ (r & 15)) << 4)) = w;
+          }
+        }
+      }
+    };
+    // parked UB row of the finished group -> UB (candidate) / -inf (cannot reach e^-margin of the row's best)
+    auto mark_group = [&](int64_t gi, uint32_t parity) {
+      const float* lb0 = slb + parity * 2 * kCRows;
+#pragma unroll 1
+      for (int t = 0; t < kCT; ++t) {
+        const int r = t * kTM + sw * 32 + lane;
+        const int64_t n = gi * kCRows + r;
+        if (n >= N) continue;
+        const float thr = fmaxf(lb0[r], lb0[kCRows + r]) - margin;
+        float* qrow = q + n * ldq;
+        float4* q4 = reinterpret_cast<float4*>(qrow);
+        int k = 0;
+        for (; k + 4 <= K; k += 4) {
+          float4 v = __ldcg(q4 + (k >> 2));
+          v.x = v.x >= thr ? v.x : -INFINITY;
+          v.y = v.y >= thr ? v.y : -INFINITY;
+          v.z = v.z >= thr ? v.z : -INFINITY;
+          v.w = v.w >= thr ? v.w : -INFINITY;
+          q4[k >> 2] = v;
+        }
+        for (; k < K; ++k) {
+          const float v = __ldcg(qrow + k);
+          qrow[k] = v >= thr ? v : -INFINITY;
+        }
+      }
+    };
+    uint32_t gcnt = 0;
+    int64_t gi = blockIdx.x, gprev = -1;
+    if (gi < ngroups) stage_group(gi);
+    named_bar_sync(1, 128);
+    for (; gi < ngroups; gi += gridDim.x, ++gcnt) {
+      // (a) staging -> TMEM A of every tile slot as soon as the previous group's MMAs released it
+      const int row = sw * 32 + lane;
+#pragma unroll 1
+      for (int s = 0; s < kCT; ++s) {
+        mbar_wait(bar(CA_FREE0 + s), (gcnt & 1) ^ 1, err);
+        tc_fence_after();
+        const unsigned char* srcT = sgen + kCOffStageA + (uint32_t)s * kCStageA + row * 256;
+        const uint32_t tA = tmem_base + ((uint32_t)(32 * sw) << 16) + 256u + kCAcol * (uint32_t)s;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint32_t rr[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 w = *reinterpret_cast<const uint4*>(srcT + (((4 * h + c) ^ (row & 15)) << 4));
+            rr[4 * c] = w.x;
+            rr[4 * c + 1] = w.y;
+            rr[4 * c + 2] = w.z;
+            rr[4 * c + 3] = w.w;
+          }
+          tmem_st16(tA + 16 * h, rr);
+        }
+        uint32_t ra[8] = {aug01, aug2, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(tA + 64u, ra);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(CA_READY0 + s));
+      }
+      named_bar_sync(1, 128);  // every stager is done reading the staging buffers
+      // (b) candidate marking of the group that just finished
+      if (gprev >= 0) {
+        const uint32_t p = (gcnt - 1) & 1;
+        mbar_wait(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
+        mark_group(gprev, p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(CL_FREE0 + p));
+      }
+      // (c) stage the next group while this one runs
+      if (gi + gridDim.x < ngroups) stage_group(gi + gridDim.x);
+      named_bar_sync(1, 128);
+      gprev = gi;
+    }
+    if (gprev >= 0) {
+      const uint32_t p = (gcnt - 1) & 1;
+      mbar_wait(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
+      mark_group(gprev, p);
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    // -------------------------------------------------------------- epilogue --
+    const int grp = (warp - 8) >> 2, quad = warp & 3;
+    const uint32_t tlane = (uint32_t)(32 * quad) << 16;
+    uint32_t icnt = 0, gcnt = 0;
+    for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
+      int64_t nrow[kCT];
+      float xn[kCT], lbmax[kCT];
+      const float* lwg[kCT];
+      const uint8_t* actg[kCT];
+#pragma unroll
+      for (int s = 0; s < kCT; ++s) {
+        const int64_t n = gi * kCRows + s * kTM + 32 * quad + lane;
+        const bool valid = n < N;
+        nrow[s] = valid ? n : -1;
+        xn[s] = valid ? __ldg(xnorm + n) : 0.f;
+        const int g = (gid != nullptr && valid) ? gid[n] : 0;
+        lwg[s] = lw + (size_t)g * K;
+        actg[s] = act != nullptr ? act + (size_t)g * K : nullptr;
+        lbmax[s] = -INFINITY;
+      }
+#pragma unroll 1
+      for (int k = 0; k < K; ++k) {
+        const float cinv2 = spar[k], ek = spar[256 + k], ea = spar[512 + k], ch = spar[768 + k];
+#pragma unroll
+        for (int s = 0; s < kCT; ++s, ++icnt) {
+          if ((int)(icnt & 1) != grp) continue;
+          const uint32_t ph = (icnt >> 1) & 1;
+          mbar_wait(bar(CT_FULL0 + grp), ph, err);
+          tc_fence_after();
+          uint32_t r[128];
+          tmem_ld64(tmem_base + tlane + 128u * grp, r);
+          tmem_ld64(tmem_base + tlane + 128u * grp + 64u, r + 64);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(CT_EMPTY0 + grp));
+          const float ss = sumsq64(r) + sumsq64(r + 64);
+          if (nrow[s] >= 0) {
+            const float d = sqrtf(ss * cinv2);
+            const float e = fmaf(ek, xn[s], ea);
+            const float dlo = fmaxf(d - e, 0.f), dhi = d + e;
+            const float c = ch + lwg[s][k];
+            float ub = fmaf(-0.5f * dlo, dlo, c), lb = fmaf(-0.5f * dhi, dhi, c);
+            ub += 1e-6f * fabsf(ub) + 1e-3f;   // fp32 rounding of the bound itself
+            lb -= 1e-6f * fabsf(lb) + 1e-3f;
+            if (actg[s] != nullptr && !actg[s][k]) ub = lb = -INFINITY;
+            q[nrow[s] * ldq + k] = ub;
+            lbmax[s] = fmaxf(lbmax[s], lb);
+          }
+        }
+      }
+      // hand the per-row maxima of the lower bounds to the stagers
+      const uint32_t p = gcnt & 1;
+      mbar_wait(bar(CL_FREE0 + p), ((gcnt >> 1) & 1) ^ 1, err);
+      float* dst = slb + (p * 2 + grp) * kCRows;
+#pragma unroll
+      for (int s = 0; s < kCT; ++s) dst[s * kTM + 32 * quad + lane] = lbmax[s];
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(CL_FULL0 + p));
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Level 3: row soft-max over the logits left in q (-inf = not a candidate):
+// q = exp(logit - log Z), Fz += sum_n log Z_n.  One warp walks four rows at a time.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, double* __restrict__ Fz) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  double fz = 0;
+  for (int64_t r0 = warp0 * 4; r0 < N; r0 += nwarps * 4) {
+    float4 v[4][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 4 * lane + 128 * j;
+        const int64_t n = r0 + u;
+        if (n < N && k < K) v[u][j] = *reinterpret_cast<const float4*>(q + n * ldq + k);
+        else v[u][j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t n = r0 + u;
+      float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = 4 * lane + 128 * (i >> 2) + (i & 3);
+        if (k >= K) e[i] = -INFINITY;
+      }
+      float mx = e[0];
+#pragma unroll
+      for (int i = 1; i < 8; ++i) mx = fmaxf(mx, e[i]);
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (n >= N) continue;
+      float se = 0.f;
+      if (mx > -INFINITY) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) se += expf(e[i] - mx);  // exp(-inf) = 0
+      }
+      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float lz = mx > -INFINITY ? logf(se) + mx : 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) e[i] = mx > -INFINITY ? expf(e[i] - lz) : 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int k = 4 * lane + 128 * j;
+        if (k + 4 <= K) {
+          *reinterpret_cast<float4*>(q + n * ldq + k) = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+        } else {
+          for (int i = 0; i < 4; ++i)
+            if (k + i < K) q[n * ldq + k + i] = e[4 * j + i];
+        }
+      }
+      if (lane == 0) fz += (double)lz;
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
+  if (lane == 0 && fz != 0.0) atomicAdd(Fz, fz);
+}
+
+// Euclidean norm of every (centred) row, D == 128: one warp per row, float4 per lane
+__global__ void __launch_bounds__(256)
+row_norm128_kernel(const float* __restrict__ X, int64_t N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t n = warp0; n < N; n += nwarps) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(X + n * kD) + lane);
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[n] = sqrtf(s);
+  }
+}
+
 }  // namespace
 
 bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
@@ -647,15 +1185,84 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err) {
   if (N <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (N + kTM - 1) / kTM;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  estep_tc128_kernel<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q, ldq,
-                                                           Fz, err);
+  estep_tc128_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q,
+                                                                  ldq, Fz, err, nullptr, nullptr, nullptr, nullptr, 0);
   return cudaGetLastError();
 }
 
+cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
+                             const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
+                             const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
+                             const int32_t* itoff, int64_t nitems, float* q, int64_t ldq, unsigned* err) {
+  if (N <= 0 || nitems <= 0) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (e != cudaSuccess) return e;
+  const int grid = (int)(nitems < sms ? nitems : sms);
+  estep_tc128_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, nullptr, q,
+                                                                 ldq, nullptr, err, lrow, koff, kcnt, itoff, nitems);
+  return cudaGetLastError();
+}
+
+cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
+                               const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
+                               const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
+                               float margin, float* q, int64_t ldq, unsigned* err) {
+  if (N <= 0) return cudaSuccess;
+  if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
+  cudaError_t e = cudaFuncSetAttribute(estep_coarse_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
+  if (e != cudaSuccess) return e;
+  const int64_t ngroups = (N + kCRows - 1) / kCRows;
+  const int grid = (int)(ngroups < sms ? ngroups : sms);
+  const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
+  estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
+                                                                   h | (h << 16), h, margin, q, ldq, err);
+  return cudaGetLastError();
+}
+
+cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, double* Fz) {
+  if (N <= 0) return cudaSuccess;
+  if (K > 256 || (ldq & 3)) return cudaErrorInvalidValue;
+  const int64_t want = (N + 31) / 32;  // 8 warps x 4 rows per CTA pass
+  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
+  estep_finalize_kernel<<<grid, 256, 0, st>>>(q, ldq, N, K, Fz);
+  return cudaGetLastError();
+}
+
+cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out) {
+  if (N <= 0) return cudaSuccess;
+  const int64_t want = (N + 7) / 8;
+  const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
+  row_norm128_kernel<<<grid, 256, 0, st>>>(X, N, out);
+  return cudaGetLastError();
+}
+
+// Host-side packing of the aug chunk of cluster k into its 4-cluster block: row i (output dimension), K slots
+// 0..2 of the 16-wide chunk (k & 3) hold the fp16 hi/mid/lo split of w[i]; same swizzled layout as the B blocks.
+// Returns the largest residual |w[i] - (h1 + h2 + h3)|.
+double tc_pack_aug(const double* w /* [128] */, int k, uint8_t* augblob) {
+  uint8_t* blk = augblob + (size_t)(k >> 2) * kTcAugBlockBytes;
+  const int j = k & 3;
+  double worst = 0;
+  for (int i = 0; i < 128; ++i) {
+    double rem = w[i];
+    for (int slot = 0; slot < 16; ++slot) {
+      __half h = __float2half_rn(0.f);
+      if (slot < 3) {
+        h = __float2half_rn((float)rem);
+        rem -= (double)__half2float(h);
+      }
+      const uint32_t kk = 16u * (uint32_t)j + (uint32_t)slot;
+      const uint32_t off = (uint32_t)i * 128u + ((((kk >> 3) ^ ((uint32_t)i & 7u))) << 4) + ((kk & 7u) << 1);
+      *reinterpret_cast<__half*>(blk + off) = h;
+    }
+    worst = std::max(worst, std::fabs(rem));
+  }
+  return worst;
+}
 
 cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
                         const long long* kcnt, long long maxcnt, long long nnz, int K, const float* cen, float scale,

@@ -16,6 +16,27 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err);
 
+// ---- two-level E step ------------------------------------------------------------------
+// level 1: one-product distances with a rigorous error bound; q[n][k] = upper bound of the logit for candidate
+//          pairs, -inf for pairs that cannot reach e^-margin of the row's best.  cpar [4][K] = {1/(s_g tau_k)^2,
+//          Ek, Ea, chat}; augblob = ceil(K/4) blocks of kTcAugBlockBytes (tc_pack_aug); aug_exp = P (A slot = 2^P)
+constexpr uint32_t kTcAugBlockBytes = 16384;
+constexpr int kTcCoarseMaxK = 256;
+cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
+                               const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
+                               const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
+                               float margin, float* q, int64_t ldq, unsigned* err);
+// level 2: exact logits of the candidate pairs (per-cluster row lists as built by nz_count/nz_scan/nz_fill with
+//          pred = kNzNotNegInf; itoff [K+1] = prefix of ceil(kcnt[k] / 128)), written into q[row][k]
+cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
+                             const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
+                             const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
+                             const int32_t* itoff, int64_t nitems, float* q, int64_t ldq, unsigned* err);
+// level 3: q = softmax over the logits in q (-inf -> 0), Fz += sum log Z
+cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, double* Fz);
+cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out);
+double tc_pack_aug(const double* w, int k, uint8_t* augblob);
+
 // Centred scatter over the per-cluster non-zero lists (see tc_kernels.cu); cen [K][128] is relative to the data
 // centre, scale a power of two with scale * max|x - c| <= 2^14.
 constexpr int kTcScatterChunk = 512;  // list rows folded into the fp32 accumulators before the fp64 add (32 tensor-core additions)
