@@ -97,6 +97,9 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   if (const char* tl = std::getenv("LCB_TC_TWO_LEVEL")) {
     if (tl[0]) use_two_level_ = tl[0] != '0';
   }
+  if (const char* mm = std::getenv("LCB_TC_MMA_MODE")) {
+    if (mm[0] >= '0' && mm[0] <= '2') tc_mma_mode_ = mm[0] - '0';
+  }
   if (const char* sg = std::getenv("LCB_TC_STAGE")) {
     if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
     else if (std::strcmp(sg, "refine") == 0) tc_stage_ = 2;
@@ -107,7 +110,7 @@ Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_, &d_aug_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_, &d_cmask_, &d_items_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
@@ -145,6 +148,7 @@ void* Engine::pinned(size_t bytes) {
 }
 
 void Engine::free_view(View& v) {
+  list_valid_ = false;
   if (v.owns_x && v.X) cudaFree(v.X);
   if (v.owns_x && v.gid) cudaFree(v.gid);
   if (v.q) cudaFree(v.q);
@@ -161,6 +165,7 @@ static void dev_alloc(void** p, size_t bytes) {
 // Make room for K responsibility columns in both buffers, keeping q's content.
 void Engine::ensure_q(View& v, int K) {
   if (K <= v.ldq && v.q && v.q2) return;
+  list_valid_ = false;
   const size_t es = prec_ == kF32 ? 4 : 8;
   int64_t nld = round_up(std::max<int64_t>(K, 1), 8);
   if (v.ldq > 0) nld = std::max(nld, std::min<int64_t>(2 * v.ldq, 512));
@@ -538,7 +543,29 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   cudaError_t ke = cudaSuccess;
   if (full) {
     // statistics over the non-zero responsibilities only: per-cluster (row, q) lists, then a gathered scatter
-    if (v.N > 0) {
+    const bool reuse = list_valid_ && list_q_ == v.q && list_K_ == K && list_N_ == v.N && prec_ == kF32 && J == 1 &&
+                       !sparse_ && use_tc_ && dev::tc_supported(D, v.ldx);
+    list_valid_ = false;
+    if (v.N > 0 && reuse) {
+      // the candidate lists of the last E pass cover every non-zero of q: gather their q (and N_k) instead of
+      // sweeping q twice more
+      long long* d_tot = (long long*)d_nzoff_.p;
+      long long* d_koff = d_tot + K;
+      const size_t rows_bytes = (size_t)round_up((int64_t)list_nnz_ * 4, 256);
+      int32_t* lrow = (int32_t*)d_list_.p;
+      float* lq = (float*)((unsigned char*)d_list_.p + rows_bytes);
+      check(dev::gather_list_q(stream_, sms_, (const float*)v.q, v.ldq, lrow, d_koff, d_tot, list_maxcnt_, K, lq, d_njk),
+            "gather_list_q");
+      ++launches_;
+      double cmax = 0;
+      for (int k = 0; k < K; ++k)
+        for (int d = 0; d < D; ++d) cmax = std::max(cmax, std::fabs(craw[(size_t)k * D + d] - centre_[d]));
+      const double span = std::max(xabs_max_ + cmax, 1e-30);
+      const float scale = (float)std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(16384.0 / span)))));
+      reserve(d_err_, 16);
+      ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, lq, d_koff, d_tot, list_maxcnt_, list_nnz_, K,
+                            (const float*)d_cen_.p, scale, d_xs, d_S, (unsigned*)d_err_.p);
+    } else if (v.N > 0) {
       const int64_t nb = dev::nz_blocks(v.N);
       reserve(d_nzcnt_, sizeof(int32_t) * (size_t)nb * K);
       reserve(d_nzoff_, sizeof(long long) * (size_t)(2 * K + 2));
@@ -622,6 +649,7 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
                       int mode, std::vector<double>* H) {
   const int J = v.J, K = v.K, D = v.D;
   const bool full = ckind_ == kGaussWish;
+  if (mode == dev::kEWrite) list_valid_ = false;
   if (mode == dev::kEWrite && prec_ == kF32 && full && use_tc_ && dev::tc_supported(D, v.ldx) && v.N > 0)
     return ephase_tc(v, weights, clusters);
   const size_t es = prec_ == kF32 ? 4 : 8;
@@ -879,14 +907,32 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
     ++launches_;
   }
   float* q = (float*)v.q;
-  check(cudaEventRecord(ev_[4], stream_), "event");
-  check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
-                                d_act, sg, aug_exp, kMargin, q, v.ldq, d_err),
-        "estep_coarse_tc128 launch");
-  ++launches_;
-  check(cudaEventRecord(ev_[5], stream_), "event");
+  const int W = (K + 31) / 32;
+  reserve(d_cmask_, sizeof(uint32_t) * (size_t)std::max<int64_t>(v.N, 1) * W);
+  uint32_t* cmask = (uint32_t*)d_cmask_.p;
+  for (int attempt = 0;; ++attempt) {
+    check(cudaEventRecord(ev_[4], stream_), "event");
+    check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
+                                  d_act, sg, aug_exp, kMargin, tc_mma_mode_, q, v.ldq, cmask, coarse_sbase_hint_, d_err),
+          "estep_coarse_tc128 launch");
+    ++launches_;
+    check(cudaEventRecord(ev_[5], stream_), "event");
+    if (coarse_hint_ok_) break;
+    // first launch on this engine: the kernel reports the shared-memory base it expected as a parameter
+    unsigned rep[2] = {0, 0};
+    check(cudaMemcpyAsync(rep, d_err, sizeof(rep), cudaMemcpyDeviceToHost, stream_), "D2H err");
+    sync();
+    if (!(rep[1] & 0x80000000u)) {
+      coarse_hint_ok_ = true;
+      break;
+    }
+    if (attempt > 0) throw_runtime("estep_coarse_tc128: shared-memory base does not settle");
+    coarse_sbase_hint_ = rep[1] & 0x7fffffffu;
+    check(cudaMemsetAsync(d_err, 0, 8, stream_), "memset");
+  }
   estep_detail_[5] = 1;
   if (tc_stage_ == 1) {
+    check(dev::apply_candidate_mask(stream_, q, v.ldq, v.N, K, cmask), "apply_candidate_mask");
     for (int i = 6; i <= 8; ++i) check(cudaEventRecord(ev_[i], stream_), "event");
     return true;
   }
@@ -898,19 +944,20 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
   long long* d_tot = (long long*)d_nzoff_.p;
   long long* d_koff = d_tot + K;
   int32_t* d_itoff = (int32_t*)(d_koff + K + 2);
-  check(dev::nz_count<float>(stream_, q, v.ldq, v.N, K, nullptr, nullptr, d_cnt, nullptr, dev::kNzNotNegInf), "nz_count");
+  check(dev::mask_count(stream_, cmask, v.N, K, d_cnt), "mask_count");
   check(dev::nz_scan(stream_, d_cnt, nb, K, d_tot), "nz_scan");
   launches_ += 2;
   std::vector<long long> tot(K), koff(K);
   check(cudaMemcpyAsync(tot.data(), d_tot, sizeof(long long) * K, cudaMemcpyDeviceToHost, stream_), "D2H candidate totals");
   sync();
   std::vector<int32_t> itoff(K + 1);
-  long long npairs = 0, nitems = 0;
+  long long npairs = 0, nitems = 0, maxcnt = 0;
   for (int k = 0; k < K; ++k) {
     koff[k] = npairs;
     itoff[k] = (int32_t)nitems;
     npairs += tot[k];
     nitems += (tot[k] + 127) / 128;
+    maxcnt = std::max(maxcnt, tot[k]);
   }
   itoff[K] = (int32_t)nitems;
   estep_detail_[4] = (double)npairs;
@@ -923,23 +970,35 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
   }
   check(cudaMemcpyAsync(d_koff, koff.data(), sizeof(long long) * K, cudaMemcpyHostToDevice, stream_), "H2D koff");
   check(cudaMemcpyAsync(d_itoff, itoff.data(), sizeof(int32_t) * (K + 1), cudaMemcpyHostToDevice, stream_), "H2D itoff");
-  reserve(d_list_, (size_t)std::max<long long>(npairs, 1) * 4 + 256);
+  // room for the row lists and, behind them, the responsibilities the statistics pass gathers later
+  const size_t rows_bytes = (size_t)round_up((int64_t)std::max<long long>(npairs, 1) * 4, 256);
+  reserve(d_list_, 2 * rows_bytes + 256);
+  reserve(d_items_, 16 * (size_t)std::max<long long>(nitems, 1));
   int32_t* lrow = (int32_t*)d_list_.p;
-  check(dev::nz_fill<float>(stream_, q, v.ldq, v.N, K, nullptr, nullptr, d_cnt, d_koff, lrow, nullptr, dev::kNzNotNegInf), "nz_fill");
+  check(dev::mask_fill(stream_, cmask, v.N, K, d_cnt, d_koff, lrow), "mask_fill");
   ++launches_;
   check(cudaEventRecord(ev_[6], stream_), "event");
   check(dev::estep_tc128_list(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw, lrow,
-                              d_koff, d_tot, d_itoff, nitems, q, v.ldq, d_err),
+                              d_koff, d_tot, d_itoff, nitems, d_items_.p, q, v.ldq, d_err),
         "estep_tc128_list launch");
-  ++launches_;
+  launches_ += 2;
   check(cudaEventRecord(ev_[7], stream_), "event");
   if (tc_stage_ == 2) {
+    check(dev::apply_candidate_mask(stream_, q, v.ldq, v.N, K, cmask), "apply_candidate_mask");
     check(cudaEventRecord(ev_[8], stream_), "event");
     return true;
   }
-  check(dev::estep_finalize(stream_, sms_, q, v.ldq, v.N, K, d_fz), "estep_finalize");
+  check(dev::estep_finalize(stream_, sms_, q, v.ldq, v.N, K, cmask, d_fz), "estep_finalize");
   ++launches_;
   check(cudaEventRecord(ev_[8], stream_), "event");
+  if (v.J == 1 && !sparse_ && npairs > 0) {
+    list_valid_ = true;
+    list_q_ = v.q;
+    list_K_ = K;
+    list_N_ = v.N;
+    list_nnz_ = npairs;
+    list_maxcnt_ = maxcnt;
+  }
   return true;
 }
 
@@ -1036,6 +1095,7 @@ bool Engine::prune(View& v, std::vector<WeightPost>& weights, std::vector<Cluste
     if (!(clusters[k].getN() < kZeroCutoff)) keep.push_back(k);
   if ((int)keep.size() == K) return false;
   if (verbose_) std::cout << '*' << std::flush;
+  list_valid_ = false;
   std::vector<ClusterPost> nc;
   std::vector<std::vector<double>> nh;
   for (int32_t k : keep) {
@@ -1184,6 +1244,7 @@ bool Engine::split_gr(View& v, std::vector<WeightPost>& weights, std::vector<Clu
     if (anyempty(cspl)) continue;
 
     // augment the labels of the whole data set (auglabels, comutils.cpp:75-104)
+    list_valid_ = false;
     ensure_q(v, K + 1);
     if (prec_ == kF32) {
       check(dev::copy_q<float>(stream_, (const float*)v.q, (float*)v.q2, v.ldq, v.ldq, v.N, K, K + 1), "copy_q");
@@ -1252,6 +1313,7 @@ void Engine::learn(int model, double prior, double wprior, int maxclusters, bool
   check(cudaSetDevice(device_), "cudaSetDevice");
   model_init(model, prior, wprior, sparse);
   verbose_ = verbose;
+  list_valid_ = false;
   ensure_q(main_, 1);
   if (prec_ == kF32) check(dev::fill_ones<float>(stream_, (float*)main_.q, main_.ldq, main_.N), "fill_ones");
   else check(dev::fill_ones<double>(stream_, (double*)main_.q, main_.ldq, main_.N), "fill_ones");
@@ -1282,6 +1344,7 @@ void Engine::set_qz(const double* q0, int K) {
   if (K < 1 || q0 == nullptr) throw_invalid("set_qz: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
   main_.K = 0;
+  list_valid_ = false;
   ensure_q(main_, K);
   const int64_t chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (8 * (int64_t)K));
   reserve(d_tmp_, sizeof(double) * chunk * K);
@@ -1306,6 +1369,7 @@ void Engine::set_labels_device(const int32_t* labels, int K) {
   if (K < 1 || labels == nullptr) throw_invalid("set_labels: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
   main_.K = 0;
+  list_valid_ = false;
   ensure_q(main_, K);
   if (prec_ == kF32) check(dev::labels_to_q<float>(stream_, labels, (float*)main_.q, main_.ldq, main_.N, K), "labels_to_q");
   else check(dev::labels_to_q<double>(stream_, labels, (double*)main_.q, main_.ldq, main_.N, K), "labels_to_q");

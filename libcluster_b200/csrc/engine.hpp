@@ -113,7 +113,10 @@ class Engine {
   // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
   bool use_two_level_ = true;
   int tc_stage_ = 0;            // 0 full, 1 stop after level 1, 2 stop after level 2
+  int tc_mma_mode_ = 0;         // MMA issue order of level 1 (tc_kernels.cu: kMma*); LCB_TC_MMA_MODE overrides
   int two_level_skip_ = 0;      // iterations left before the two-level path is tried again after it did not pay
+  uint32_t coarse_sbase_hint_ = 1024;  // shared-memory base the level-1 kernel takes as a parameter (tc_kernels.cuh)
+  bool coarse_hint_ok_ = false;
   double estep_detail_[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   cudaStream_t stream_ = nullptr;
   View main_;
@@ -137,7 +140,13 @@ class Engine {
   bool hints_first_ = false;  // first iteration takes its statistic centres from the hints
 
   // device scratch
-  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_, d_err_, d_aug_;
+  DeviceBuf d_RT_, d_mhi_, d_mlo_, d_chat_, d_lw_, d_act_, d_cen_, d_stats_, d_small_, d_tmp_, d_mean_, d_tc_, d_nzcnt_, d_nzoff_, d_list_, d_err_, d_cmask_, d_items_;
+  // per-cluster row lists left by the two-level E pass; the next statistics pass reuses them while q is untouched
+  bool list_valid_ = false;
+  const void* list_q_ = nullptr;
+  int list_K_ = 0;
+  int64_t list_N_ = 0;
+  long long list_nnz_ = 0, list_maxcnt_ = 0;
   std::vector<uint8_t> act_;  // host copy of the sparse mask (J*K), empty if unused
   void* h_pin_ = nullptr;
   size_t h_pin_bytes_ = 0;

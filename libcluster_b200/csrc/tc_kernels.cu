@@ -82,6 +82,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
     }
   }
 }
+// The same for warps that wait a long time by design (stagers, producers): back off so that the polling does not
+// take issue slots from the warps that share the scheduler.
+__device__ __forceinline__ void mbar_wait_patient(uint32_t bar, uint32_t parity, unsigned* err) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0;; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    if (spin > 2) __nanosleep(spin < 64 ? 32 : 256);
+    if (spin > (1u << 21)) {
+      if (err) atomicExch(err, 0xdead0000u | (bar & 0xffffu));
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -111,6 +131,20 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
         : "memory");
   }
 }
+// The same with the shared-memory descriptor given as two 32-bit words (lo = start address field | LBO, hi = SBO,
+// version, swizzle): the issuing warp then advances a descriptor with one 32-bit uniform add.
+__device__ __forceinline__ void tc_mma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 bd, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
 // shared-memory matrix descriptor: K-major, 128-byte swizzle, 8-row groups 1024 B apart
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -223,8 +257,8 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
                    const uint8_t* __restrict__ blob, const float* __restrict__ ascale,
                    const float* __restrict__ inv_t2, const float* __restrict__ chat, const float* __restrict__ lw,
                    const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq, double* __restrict__ Fz,
-                   unsigned* __restrict__ err, const int32_t* __restrict__ lrow, const long long* __restrict__ koff,
-                   const long long* __restrict__ kcnt, const int32_t* __restrict__ itoff, int64_t nitems) {
+                   unsigned* __restrict__ err, const int32_t* __restrict__ lrow, const int4* __restrict__ items,
+                   int64_t nitems) {
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
@@ -272,7 +306,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         int k0 = 0, k1 = K;
         if constexpr (kList) {
-          k0 = list_item(tile, K, itoff, koff, kcnt).k;
+          k0 = __ldg(items + tile).x;
           k1 = k0 + 1;
         }
         for (int k = k0; k < k1; ++k, ++cnt) {
@@ -334,16 +368,30 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     const int ew = warp - 4;
     double fz = 0;
     uint32_t cnt = 0;
+    // list mode: (cluster, row) of this thread for the next item are fetched one item ahead
+    int nk = 0;
+    int64_t nn = -1;
+    auto fetch = [&](int64_t it) {
+      nk = 0;
+      nn = -1;
+      if (it < ntiles) {
+        const int4 item = __ldg(items + it);
+        nk = item.x;
+        if (ew * 32 + lane < item.y)
+          nn = (int64_t)__ldg(lrow + (((long long)(unsigned)item.z) | ((long long)item.w << 32)) + ew * 32 + lane);
+      }
+    };
+    if constexpr (kList) fetch(blockIdx.x);
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t n = tile * kTM + ew * 32 + lane;
       bool valid = n < N;
       int k0 = 0, k1 = K;
       if constexpr (kList) {
-        const ListItem item = list_item(tile, K, itoff, koff, kcnt);
-        k0 = item.k;
+        k0 = nk;
         k1 = k0 + 1;
-        valid = ew * 32 + lane < item.count;
-        n = valid ? (int64_t)__ldg(lrow + item.base + ew * 32 + lane) : 0;
+        valid = nn >= 0;
+        n = valid ? nn : 0;
+        fetch(tile + gridDim.x);
       }
       const int g = (gid != nullptr && valid) ? gid[n] : 0;
       const float* lwg = lw + (size_t)g * K;
@@ -396,14 +444,30 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     const int quad = warp & 3, kb = (warp - 8) >> 2;
     const int row = 32 * quad + lane;
     uint32_t cnt = 0;
+    // list mode: the (cluster, row) of this thread are fetched two items ahead and the rows of the next item are
+    // prefetched into L2 while the current one is built (the gather is latency-bound otherwise)
+    int k_cur = 0, k_nx = 0;
+    int64_t n_cur = N, n_nx = N;
+    auto fetch = [&](int64_t it, int& kk, int64_t& nn) {
+      kk = 0;
+      nn = N;
+      if (it < ntiles) {
+        const int4 item = __ldg(items + it);
+        kk = item.x;
+        if (row < item.y) nn = (int64_t)__ldg(lrow + (((long long)(unsigned)item.z) | ((long long)item.w << 32)) + row);
+      }
+    };
+    if constexpr (kList) {
+      fetch(blockIdx.x, k_cur, n_cur);
+      fetch((int64_t)blockIdx.x + gridDim.x, k_nx, n_nx);
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t n = tile * kTM + row;
       int k0 = 0, k1 = K;
       if constexpr (kList) {
-        const ListItem item = list_item(tile, K, itoff, koff, kcnt);
-        k0 = item.k;
+        k0 = k_cur;
         k1 = k0 + 1;
-        n = row < item.count ? (int64_t)__ldg(lrow + item.base + row) : N;
+        n = n_cur;
       }
       float4 x[16];
       if (n < N) {
@@ -413,6 +477,16 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if constexpr (kList) {
+        if (n_nx < N) {
+          const float* nxt = X + n_nx * kD + 64 * kb;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
+        }
+        k_cur = k_nx;
+        n_cur = n_nx;
+        fetch(tile + 2 * (int64_t)gridDim.x, k_nx, n_nx);
       }
       for (int k = k0; k < k1; ++k, ++cnt) {
         const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
@@ -707,9 +781,9 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
 //     | d~ - d | <= E_nk = Ek[k] * |x_n| + Ea[k],     d = | R_k (x_n - m_k) |
 // so each logit is bracketed, LB <= logit <= UB.  A pair (n, k) is a *candidate*
 // iff UB_nk >= max_j LB_nj - margin; only candidates can have q > e^-margin.  The
-// kernel leaves UB (candidates) or -inf (others) in q; level 2 (the list mode of
-// estep_tc128_kernel) recomputes the candidates at fp32-equivalent accuracy and
-// estep_finalize_kernel forms q and log Z.
+// kernel leaves UB in q and the candidates as a bit mask per row (cmask); level 2
+// (the list mode of estep_tc128_kernel) recomputes the candidates at
+// fp32-equivalent accuracy and estep_finalize_kernel forms q and log Z.
 //
 // One persistent CTA per SM works on groups of kCT = 3 tiles (384 rows) so that a
 // cluster's operand, streamed from L2 by the TMA engine, is used by three MMAs
@@ -739,6 +813,12 @@ constexpr uint32_t kCOffLb = kCOffPar + 4 * 256 * 4;           // 208896: [2 par
 constexpr uint32_t kCOffBar = kCOffLb + 2 * 2 * kCRows * 4;    // 215040
 constexpr uint32_t kCSmemBytes = kCOffBar + 512 + 1024;
 constexpr uint32_t kCAcol = 72;                                // TMEM columns of one A slot
+// Order and shapes of the MMAs of one (cluster, tile) item.  R_k is lower-triangular, so the K chunk of input
+// dimensions [16c, 16c+16) only feeds output columns >= 16c.
+//   kMmaShrink8    eight chunks with N = 128 - 16c: least tensor work (4.5 full-width MMAs), eight changes of shape
+//   kMmaTwoShapes  chunks 0-3 at N = 128, chunks 4-7 at N = 64: 6 full-width MMAs, two shapes
+//   kMmaSplitHalves columns [0,64) and [64,128) as two independent accumulate chains, issued alternately
+enum { kMmaShrink8 = 0, kMmaTwoShapes = 1, kMmaSplitHalves = 2 };
 enum {
   CB_FULL0 = 0, CB_EMPTY0 = 3, CG_FULL0 = 6, CG_EMPTY0 = 8, CA_READY0 = 10, CA_FREE0 = 13, CT_FULL0 = 16, CT_EMPTY0 = 18,
   CL_FULL0 = 20, CL_FREE0 = 22, C_COUNT = 24
@@ -769,11 +849,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
 }
 // sum of squares of 64 fp32 register values with packed FMAs, four independent chains
 __device__ __forceinline__ float sumsq64(const uint32_t* r) {
-  unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+  unsigned long long acc[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-  for (int i = 0; i < 64; i += 8) {
+  for (int i = 0; i < 64; i += 16) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
+    for (int c = 0; c < 8; ++c) {
       unsigned long long p;
       asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "r"(r[i + 2 * c]), "r"(r[i + 2 * c + 1]));
       asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc[c]) : "l"(p));
@@ -781,7 +861,7 @@ __device__ __forceinline__ float sumsq64(const uint32_t* r) {
   }
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 8; ++c) {
     uint32_t a, b;
     asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(acc[c]));
     s += __uint_as_float(a) + __uint_as_float(b);
@@ -797,20 +877,33 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
                           const int32_t* __restrict__ gid, int K, const uint8_t* __restrict__ blob,
                           const uint8_t* __restrict__ augblob, const float* __restrict__ cpar /* [4][K] */,
                           const float* __restrict__ lw, const uint8_t* __restrict__ act, float sg, uint32_t aug01,
-                          uint32_t aug2, float margin, float* __restrict__ q, int64_t ldq, unsigned* __restrict__ err) {
+                          uint32_t aug2, float margin, int mma_mode, float* __restrict__ q, int64_t ldq,
+                          uint32_t* __restrict__ cmask, uint32_t sbase_hint, unsigned* __restrict__ err) {
   extern __shared__ unsigned char smem_dyn[];
-  const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  // opaque copies: the compiler would otherwise rematerialise these from special registers (S2R / S2UR, ~50 cycles
+  // each) inside the per-item loops, where registers are tight
+  uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+  asm volatile("" : "+r"(sbase));
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
+  asm volatile("" : "+l"(sgen));
   const uint32_t sBar = sbase + kCOffBar;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT);
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
   float* spar = reinterpret_cast<float*>(sgen + kCOffPar);  // [0] cinv2, [1] Ek, [2] Ea, [3] chat; stride 256
   float* slb = reinterpret_cast<float*>(sgen + kCOffLb);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t tid = threadIdx.x;
+  asm volatile("" : "+r"(tid));
+  // The MMA warp addresses shared memory through sbase_hint, a kernel parameter (so that its address arithmetic
+  // stays in uniform registers); a wrong hint is reported through err[1] and the host relaunches with the right one.
+  if (sbase != sbase_hint) {
+    if (tid == 0 && blockIdx.x == 0) err[1] = 0x80000000u | sbase;
+    return;
+  }
+  const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   const int64_t ngroups = (N + kCRows - 1) / kCRows;
 
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) {
       mbar_init(bar(CB_FULL0 + i), 1);
       mbar_init(bar(CB_EMPTY0 + i), 1);
@@ -827,9 +920,11 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 4 * 256; i += kThreadsTc) {
+  for (int i = (int)tid; i < 4 * 256; i += kThreadsTc) {
     const int a = i >> 8, k = i & 255;
-    spar[i] = k < K ? cpar[(size_t)a * K + k] : 0.f;
+    float val = k < K ? cpar[(size_t)a * K + k] : 0.f;
+    if (a == 3 && gid == nullptr && k < K) val += lw[k];  // single group: fold E[log pi_k] into the constant
+    spar[i] = val;
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -841,10 +936,15 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  uint32_t tmem_base = *tmem_slot;
+  asm volatile("" : "+r"(tmem_base));
+  const bool tmem_ok = tmem_base == 0;  // all 512 columns are ours, so the allocation starts at column 0, lane 0
+  if (!tmem_ok && tid == 0) atomicExch(err, 0xdead7e00u);
 
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+  if (!tmem_ok) {
+    // nothing: fall through to the dealloc
+  } else if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 0 && lane == 0) {
       // ---------------------------------------------------------- producer --
       uint32_t bcnt = 0, acnt = 0;
@@ -852,14 +952,14 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
         for (int k = 0; k < K; ++k, ++bcnt) {
           if ((k & 3) == 0) {
             const uint32_t as = acnt & 1, aph = (acnt >> 1) & 1;
-            mbar_wait(bar(CG_EMPTY0 + as), aph ^ 1, err);
+            mbar_wait_patient(bar(CG_EMPTY0 + as), aph ^ 1, err);
             mbar_expect_tx(bar(CG_FULL0 + as), kTcAugBlockBytes);
             bulk_g2s(sbase + kCOffAug + as * kTcAugBlockBytes, augblob + (size_t)(k >> 2) * kTcAugBlockBytes,
                      kTcAugBlockBytes, bar(CG_FULL0 + as));
             ++acnt;
           }
           const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
-          mbar_wait(bar(CB_EMPTY0 + bs), bph ^ 1, err);
+          mbar_wait_patient(bar(CB_EMPTY0 + bs), bph ^ 1, err);
           mbar_expect_tx(bar(CB_FULL0 + bs), kCBStage);
           const uint8_t* src = blob + (size_t)k * kBBlob;
           bulk_g2s(sbase + bs * kCBStage, src, 16384u, bar(CB_FULL0 + bs));                  // hi, dims 0..63
@@ -869,53 +969,82 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     }
     if (warp == 1) {
       // -------------------------------------------------------- MMA issuer --
-      uint32_t bcnt = 0, acnt = 0, icnt = 0, gcnt = 0, as = 0;
+      // Every address below derives from kernel parameters, constants and the loop counters only (TMEM base = 0:
+      // this CTA owns all 512 columns; shared-memory base = sbase_hint), so the whole loop runs on the uniform
+      // datapath; the first version spent ~900 cycles per item moving values from vector to uniform registers.
+      const uint32_t sb = sbase_hint;
+      const uint32_t barb = sb + kCOffBar;
+      uint32_t icnt = 0, gcnt = 0, acnt = 0;
+      uint32_t bs = 0, bph = 0, as = 0;
       for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
-        for (int k = 0; k < K; ++k, ++bcnt) {
-          const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
+        for (int k = 0; k < K; ++k) {
           if ((k & 3) == 0) {
             as = acnt & 1;
-            mbar_wait(bar(CG_FULL0 + as), (acnt >> 1) & 1, err);
+            mbar_wait(barb + 8u * (CG_FULL0 + as), (acnt >> 1) & 1, err);
             ++acnt;
           }
-          mbar_wait(bar(CB_FULL0 + bs), bph, err);
-          const uint32_t sBk = sbase + bs * kCBStage;
-          const uint64_t db0 = umma_desc(sBk), db1 = umma_desc(sBk + 16384u);
-          const uint64_t dbg = umma_desc(sbase + kCOffAug + as * kTcAugBlockBytes) + (uint64_t)(2 * (k & 3));
+          mbar_wait(barb + 8u * (CB_FULL0 + bs), bph, err);
+          const uint32_t lo0 = umma_desc_lo(sb + bs * kCBStage), lo1 = lo0 + (16384u >> 4);
+          const uint32_t log_ = umma_desc_lo(sb + kCOffAug + as * kTcAugBlockBytes) + 2u * (uint32_t)(k & 3);
           const bool last_k = k == K - 1;
-#pragma unroll 1
+#pragma unroll
           for (int s = 0; s < kCT; ++s, ++icnt) {
             const uint32_t a = icnt & 1, ph = (icnt >> 1) & 1;
-            if (k == 0) mbar_wait(bar(CA_READY0 + s), gcnt & 1, err);
-            mbar_wait(bar(CT_EMPTY0 + a), ph ^ 1, err);
+            if (k == 0) mbar_wait(barb + 8u * (CA_READY0 + s), gcnt & 1, err);
+            mbar_wait(barb + 8u * (CT_EMPTY0 + a), ph ^ 1, err);
             tc_fence_after();
-            const uint32_t d0 = tmem_base + 128u * a;
-            const uint32_t a0 = tmem_base + 256u + kCAcol * (uint32_t)s;
+            const uint32_t d0 = 128u * a;
+            const uint32_t a0 = 256u + kCAcol * (uint32_t)s;
             if (elect_one()) {
-              // accumulator = -s_g tau_k R_k m_k (aug chunk), then the 8 triangular chunks
-              tc_mma_f16_ts(d0, a0 + 64u, dbg, umma_idesc(128), 0u);
+              // accumulator = -s_g tau_k R_k m_k (aug chunk), then the triangular chunks; see kMma* above
+              tc_mma_f16_ts_w(d0, a0 + 64u, log_, kDescHi, umma_idesc(128), 0u);
+              if (mma_mode == kMmaShrink8) {
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
-                const int kb = c >> 2, c4 = c & 3;
-                const uint64_t off = (uint64_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
-                tc_mma_f16_ts(d0 + 16 * c, a0 + 8 * c, (kb ? db1 : db0) + off, umma_idesc(128 - 16 * c), 1u);
+                for (int c = 0; c < 8; ++c) {
+                  const int kb = c >> 2, c4 = c & 3;
+                  const uint32_t off = (uint32_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
+                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, (kb ? lo1 : lo0) + off, kDescHi, umma_idesc(128 - 16 * c), 1u);
+                }
+              } else if (mma_mode == kMmaTwoShapes) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const int kb = c >> 2, c4 = c & 3;
+                  tc_mma_f16_ts_w(d0 + 64 * kb, a0 + 8 * c, (kb ? lo1 : lo0) + (uint32_t)((32 * c4) >> 4), kDescHi,
+                                  umma_idesc(128 - 64 * kb), 1u);
+                }
+              } else {
+                // columns [0,64) and [64,128) are independent accumulators: alternate between them
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                  tc_mma_f16_ts_w(d0 + 64, a0 + 8 * c, lo0 + (uint32_t)((64 * 128 + 32 * c) >> 4), kDescHi, umma_idesc(64), 1u);
+                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, lo0 + (uint32_t)((16 * c * 128 + 32 * c) >> 4), kDescHi,
+                                  umma_idesc(64 - 16 * c), 1u);
+                }
+#pragma unroll
+                for (int c = 4; c < 8; ++c)
+                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, lo1 + (uint32_t)(((16 * c - 64) * 128 + 32 * (c - 4)) >> 4), kDescHi,
+                                  umma_idesc(128 - 16 * c), 1u);
               }
-              tc_commit(bar(CT_FULL0 + a));
-              if (last_k) tc_commit(bar(CA_FREE0 + s));
+              tc_commit(barb + 8u * (CT_FULL0 + a));
+              if (last_k) tc_commit(barb + 8u * (CA_FREE0 + s));
             }
             __syncwarp();
           }
           const bool aug_done = (k & 3) == 3 || last_k;
           if (elect_one()) {
-            tc_commit(bar(CB_EMPTY0 + bs));
-            if (aug_done) tc_commit(bar(CG_EMPTY0 + as));
+            tc_commit(barb + 8u * (CB_EMPTY0 + bs));
+            if (aug_done) tc_commit(barb + 8u * (CG_EMPTY0 + as));
           }
           __syncwarp();
+          if (++bs == kCStages) {
+            bs = 0;
+            bph ^= 1;
+          }
         }
       }
     }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // --------------------------------------------------------------- stagers --
     const int sw = warp - 4;  // == lane quadrant of the TMEM rows this warp may touch
     // X rows of group gi -> fp16(s_g x) in the staging buffers; a warp converts two rows per step
@@ -951,30 +1080,35 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
         }
       }
     };
-    // parked UB row of the finished group -> UB (candidate) / -inf (cannot reach e^-margin of the row's best)
+    // parked UB row of the finished group -> candidate bit mask (bit k of row n: UB_nk can reach e^-margin of the
+    // row's best lower bound)
     auto mark_group = [&](int64_t gi, uint32_t parity) {
       const float* lb0 = slb + parity * 2 * kCRows;
+      const int W = (K + 31) >> 5;
 #pragma unroll 1
       for (int t = 0; t < kCT; ++t) {
         const int r = t * kTM + sw * 32 + lane;
         const int64_t n = gi * kCRows + r;
         if (n >= N) continue;
         const float thr = fmaxf(lb0[r], lb0[kCRows + r]) - margin;
-        float* qrow = q + n * ldq;
-        float4* q4 = reinterpret_cast<float4*>(qrow);
-        int k = 0;
+        const float* qrow = q + n * ldq;
+        const float4* q4 = reinterpret_cast<const float4*>(qrow);
+        uint32_t* mrow = cmask + n * W;
+        uint32_t word = 0;
+        int k = 0, wi = 0;
         for (; k + 4 <= K; k += 4) {
-          float4 v = __ldcg(q4 + (k >> 2));
-          v.x = v.x >= thr ? v.x : -INFINITY;
-          v.y = v.y >= thr ? v.y : -INFINITY;
-          v.z = v.z >= thr ? v.z : -INFINITY;
-          v.w = v.w >= thr ? v.w : -INFINITY;
-          q4[k >> 2] = v;
+          const float4 v = __ldcg(q4 + (k >> 2));
+          const uint32_t b = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
+          word |= b << (k & 31);
+          if ((k & 31) == 28) {
+            mrow[wi++] = word;
+            word = 0;
+          }
         }
         for (; k < K; ++k) {
-          const float v = __ldcg(qrow + k);
-          qrow[k] = v >= thr ? v : -INFINITY;
+          if (__ldcg(qrow + k) >= thr) word |= 1u << (k & 31);
         }
+        if (K & 31) mrow[wi] = word;
       }
     };
     uint32_t gcnt = 0;
@@ -986,7 +1120,7 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       const int row = sw * 32 + lane;
 #pragma unroll 1
       for (int s = 0; s < kCT; ++s) {
-        mbar_wait(bar(CA_FREE0 + s), (gcnt & 1) ^ 1, err);
+        mbar_wait_patient(bar(CA_FREE0 + s), (gcnt & 1) ^ 1, err);
         tc_fence_after();
         const unsigned char* srcT = sgen + kCOffStageA + (uint32_t)s * kCStageA + row * 256;
         const uint32_t tA = tmem_base + ((uint32_t)(32 * sw) << 16) + 256u + kCAcol * (uint32_t)s;
@@ -1014,7 +1148,7 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       // (b) candidate marking of the group that just finished
       if (gprev >= 0) {
         const uint32_t p = (gcnt - 1) & 1;
-        mbar_wait(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
+        mbar_wait_patient(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
         mark_group(gprev, p);
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(CL_FREE0 + p));
@@ -1026,17 +1160,19 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     }
     if (gprev >= 0) {
       const uint32_t p = (gcnt - 1) & 1;
-      mbar_wait(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
+      mbar_wait_patient(bar(CL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
       mark_group(gprev, p);
     }
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // -------------------------------------------------------------- epilogue --
     const int grp = (warp - 8) >> 2, quad = warp & 3;
-    const uint32_t tlane = (uint32_t)(32 * quad) << 16;
+    const uint32_t tacc = tmem_base + ((uint32_t)(32 * quad) << 16) + 128u * (uint32_t)grp;
+    const uint32_t bfull = bar(CT_FULL0 + grp), bempty = bar(CT_EMPTY0 + grp);
+    const bool grouped = gid != nullptr;
     uint32_t icnt = 0, gcnt = 0;
     for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
-      int64_t nrow[kCT];
+      float* qrow[kCT];
       float xn[kCT], lbmax[kCT];
       const float* lwg[kCT];
       const uint8_t* actg[kCT];
@@ -1044,9 +1180,9 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       for (int s = 0; s < kCT; ++s) {
         const int64_t n = gi * kCRows + s * kTM + 32 * quad + lane;
         const bool valid = n < N;
-        nrow[s] = valid ? n : -1;
+        qrow[s] = valid ? q + n * ldq : nullptr;
         xn[s] = valid ? __ldg(xnorm + n) : 0.f;
-        const int g = (gid != nullptr && valid) ? gid[n] : 0;
+        const int g = (grouped && valid) ? gid[n] : 0;
         lwg[s] = lw + (size_t)g * K;
         actg[s] = act != nullptr ? act + (size_t)g * K : nullptr;
         lbmax[s] = -INFINITY;
@@ -1057,27 +1193,30 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
 #pragma unroll
         for (int s = 0; s < kCT; ++s, ++icnt) {
           if ((int)(icnt & 1) != grp) continue;
-          const uint32_t ph = (icnt >> 1) & 1;
-          mbar_wait(bar(CT_FULL0 + grp), ph, err);
+          // everything that does not depend on the accumulator first: its latency hides behind the wait
+          float c = ch;
+          if (grouped) c += __ldg(lwg[s] + k);
+          const bool off = actg[s] != nullptr && !__ldg(actg[s] + k);
+          const float e = fmaf(ek, xn[s], ea);
+          mbar_wait(bfull, (icnt >> 1) & 1, err);
           tc_fence_after();
           uint32_t r[128];
-          tmem_ld64(tmem_base + tlane + 128u * grp, r);
-          tmem_ld64(tmem_base + tlane + 128u * grp + 64u, r + 64);
+          tmem_ld64(tacc, r);
+          tmem_ld64(tacc + 64u, r + 64);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar(CT_EMPTY0 + grp));
+          if (lane == 0) mbar_arrive(bempty);
           const float ss = sumsq64(r) + sumsq64(r + 64);
-          if (nrow[s] >= 0) {
-            const float d = sqrtf(ss * cinv2);
-            const float e = fmaf(ek, xn[s], ea);
+          if (qrow[s] != nullptr) {
+            float d;
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(ss * cinv2));
             const float dlo = fmaxf(d - e, 0.f), dhi = d + e;
-            const float c = ch + lwg[s][k];
             float ub = fmaf(-0.5f * dlo, dlo, c), lb = fmaf(-0.5f * dhi, dhi, c);
-            ub += 1e-6f * fabsf(ub) + 1e-3f;   // fp32 rounding of the bound itself
-            lb -= 1e-6f * fabsf(lb) + 1e-3f;
-            if (actg[s] != nullptr && !actg[s][k]) ub = lb = -INFINITY;
-            q[nrow[s] * ldq + k] = ub;
+            ub += 2e-6f * fabsf(ub) + 1e-3f;   // fp32 rounding of the bound itself (approximate square root)
+            lb -= 2e-6f * fabsf(lb) + 1e-3f;
+            if (off) ub = lb = -INFINITY;
+            qrow[s][k] = ub;
             lbmax[s] = fmaxf(lbmax[s], lb);
           }
         }
@@ -1102,65 +1241,157 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------
-// Level 3: row soft-max over the logits left in q (-inf = not a candidate):
-// q = exp(logit - log Z), Fz += sum_n log Z_n.  One warp walks four rows at a time.
+// Level 3: row soft-max over the candidate logits in q (cmask: W words per row):
+// q = exp(logit - log Z) for candidates, 0 elsewhere; Fz += sum_n log Z_n.
+// LPR lanes share a row (NV float4 each), a warp keeps 4 * 32 / LPR rows in flight.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, double* __restrict__ Fz) {
-  const int lane = threadIdx.x & 31;
+template <int LPR, int NV>
+__global__ void __launch_bounds__(256, NV == 1 ? 4 : 2)
+estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, const uint32_t* __restrict__ cmask, int W,
+                      double* __restrict__ Fz) {
+  constexpr int RPW = 32 / LPR, U = 4;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double fz = 0;
-  for (int64_t r0 = warp0 * 4; r0 < N; r0 += nwarps * 4) {
-    float4 v[4][2];
+  for (int64_t r0 = warp0 * (U * RPW); r0 < N; r0 += nwarps * (U * RPW)) {
+    float4 v[U][NV];
+    uint32_t m[U][NV];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
+      const int64_t n = r0 + u * RPW + rsel;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = 4 * lane + 128 * j;
-        const int64_t n = r0 + u;
-        if (n < N && k < K) v[u][j] = *reinterpret_cast<const float4*>(q + n * ldq + k);
-        else v[u][j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      for (int j = 0; j < NV; ++j) {
+        const int k = 4 * sub + 4 * LPR * j;
+        if (n < N && k < K) {
+          v[u][j] = *reinterpret_cast<const float4*>(q + n * ldq + k);
+          m[u][j] = (__ldg(cmask + n * W + (k >> 5)) >> (k & 31)) & 0xFu;
+        } else {
+          v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          m[u][j] = 0u;
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int64_t n = r0 + u;
-      float e[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+    for (int u = 0; u < U; ++u) {
+      const int64_t n = r0 + u * RPW + rsel;
+      float e[4 * NV];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = 4 * lane + 128 * (i >> 2) + (i & 3);
-        if (k >= K) e[i] = -INFINITY;
+      for (int j = 0; j < NV; ++j) {
+        const int k = 4 * sub + 4 * LPR * j;
+        const float x[4] = {v[u][j].x, v[u][j].y, v[u][j].z, v[u][j].w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) e[4 * j + i] = (((m[u][j] >> i) & 1u) && k + i < K) ? x[i] : -INFINITY;
       }
       float mx = e[0];
 #pragma unroll
-      for (int i = 1; i < 8; ++i) mx = fmaxf(mx, e[i]);
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (n >= N) continue;
+      for (int i = 1; i < 4 * NV; ++i) mx = fmaxf(mx, e[i]);
+#pragma unroll
+      for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      const bool any = mx > -INFINITY;
       float se = 0.f;
-      if (mx > -INFINITY) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) se += expf(e[i] - mx);  // exp(-inf) = 0
-      }
-      for (int o = 16; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      const float lz = mx > -INFINITY ? logf(se) + mx : 0.f;
+      for (int i = 0; i < 4 * NV; ++i) se += any ? expf(e[i] - mx) : 0.f;  // exp(-inf) = 0
 #pragma unroll
-      for (int i = 0; i < 8; ++i) e[i] = mx > -INFINITY ? expf(e[i] - lz) : 0.f;
+      for (int o = LPR / 2; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+      const float lz = any ? logf(se) + mx : 0.f;
+      if (n >= N) continue;
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int k = 4 * lane + 128 * j;
+      for (int j = 0; j < NV; ++j) {
+        const int k = 4 * sub + 4 * LPR * j;
+        float o4[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o4[i] = any ? expf(e[4 * j + i] - lz) : 0.f;
         if (k + 4 <= K) {
-          *reinterpret_cast<float4*>(q + n * ldq + k) = make_float4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+          *reinterpret_cast<float4*>(q + n * ldq + k) = make_float4(o4[0], o4[1], o4[2], o4[3]);
         } else {
           for (int i = 0; i < 4; ++i)
-            if (k + i < K) q[n * ldq + k + i] = e[4 * j + i];
+            if (k + i < K) q[n * ldq + k + i] = o4[i];
         }
       }
-      if (lane == 0) fz += (double)lz;
+      if (sub == 0) fz += (double)lz;
     }
   }
   for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
   if (lane == 0 && fz != 0.0) atomicAdd(Fz, fz);
+}
+
+// q[n][k] = -inf where the candidate bit is clear (only the LCB_TC_STAGE test modes look at this)
+__global__ void __launch_bounds__(256)
+apply_mask_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, const uint32_t* __restrict__ cmask, int W) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int64_t n = i / K;
+  const int k = (int)(i - n * K);
+  if (!((cmask[n * W + (k >> 5)] >> (k & 31)) & 1u)) q[n * ldq + k] = -INFINITY;
+}
+
+// ---------------------------------------------------------------------------
+// Candidate masks -> per-cluster row lists (same block structure as nz_count / nz_fill in kernels.cu, so that
+// nz_scan serves both): counts per (row block, cluster), then the rows at their scanned offsets.
+// ---------------------------------------------------------------------------
+constexpr int kMaskBlock = 2048;  // == kNzBlock
+template <bool kFill>
+__global__ void __launch_bounds__(256)
+mask_lists_kernel(const uint32_t* __restrict__ cmask, int W, int64_t N, int K, int32_t* __restrict__ blockcnt,
+                  const long long* __restrict__ koff, int32_t* __restrict__ lrow) {
+  extern __shared__ int scnt[];
+  for (int k = threadIdx.x; k < K; k += 256) scnt[k] = 0;
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * kMaskBlock;
+  const int64_t r1 = (r0 + kMaskBlock < N) ? r0 + kMaskBlock : N;
+  for (int64_t n = r0 + threadIdx.x; n < r1; n += 256) {
+    for (int w = 0; w < W; ++w) {
+      uint32_t word = cmask[n * W + w];
+      while (word) {
+        const int b = __ffs(word) - 1;
+        word &= word - 1;
+        const int k = 32 * w + b;
+        if (k >= K) break;
+        const int pos = atomicAdd(&scnt[k], 1);
+        if (kFill) lrow[koff[k] + blockcnt[(size_t)blockIdx.x * K + k] + pos] = (int32_t)n;
+      }
+    }
+  }
+  if (!kFill) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += 256) blockcnt[(size_t)blockIdx.x * K + k] = scnt[k];
+  }
+}
+
+// Work items of level 2: 128-entry chunks of the per-cluster lists, resolved once instead of by every warp role
+__global__ void __launch_bounds__(256)
+build_items_kernel(const int32_t* __restrict__ itoff, const long long* __restrict__ koff,
+                   const long long* __restrict__ kcnt, int K, int64_t nitems, int4* __restrict__ items) {
+  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= nitems) return;
+  const ListItem r = list_item(it, K, itoff, koff, kcnt);
+  items[it] = make_int4(r.k, r.count, (int)(r.base & 0xffffffffLL), (int)(r.base >> 32));
+}
+
+// lq[e] = q[lrow[e]][k] for every entry of cluster k's list and Nk[k] = sum_e lq[e]: the statistics pass can then
+// reuse the candidate lists of the E pass instead of sweeping q again (single group, no sparse mask).
+__global__ void __launch_bounds__(256)
+gather_list_q_kernel(const float* __restrict__ q, int64_t ldq, const int32_t* __restrict__ lrow,
+                     const long long* __restrict__ koff, const long long* __restrict__ kcnt, float* __restrict__ lq,
+                     double* __restrict__ Nk) {
+  const int k = blockIdx.y;
+  const long long cnt = kcnt[k], base = koff[k];
+  double acc = 0;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
+    const float v = q[(int64_t)lrow[base + e] * ldq + k];
+    lq[base + e] = v;
+    acc += (double)v;
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int i = 0; i < 8; ++i) t += part[i];
+    if (t != 0.0) atomicAdd(&Nk[k], t);
+  }
 }
 
 // Euclidean norm of every (centred) row, D == 128: one warp per row, float4 per lane
@@ -1190,27 +1421,31 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
   const int64_t ntiles = (N + kTM - 1) / kTM;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   estep_tc128_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q,
-                                                                  ldq, Fz, err, nullptr, nullptr, nullptr, nullptr, 0);
+                                                                  ldq, Fz, err, nullptr, nullptr, 0);
   return cudaGetLastError();
 }
 
 cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                              const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                              const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
-                             const int32_t* itoff, int64_t nitems, float* q, int64_t ldq, unsigned* err) {
+                             const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err) {
   if (N <= 0 || nitems <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  build_items_kernel<<<(unsigned)((nitems + 255) / 256), 256, 0, st>>>(itoff, koff, kcnt, K, nitems, (int4*)items);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(estep_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int grid = (int)(nitems < sms ? nitems : sms);
   estep_tc128_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, nullptr, q,
-                                                                 ldq, nullptr, err, lrow, koff, kcnt, itoff, nitems);
+                                                                 ldq, nullptr, err, lrow, (const int4*)items, nitems);
   return cudaGetLastError();
 }
 
 cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
-                               float margin, float* q, int64_t ldq, unsigned* err) {
+                               float margin, int mma_mode, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
+                               unsigned* err) {
   if (N <= 0) return cudaSuccess;
   if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(estep_coarse_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
@@ -1219,16 +1454,52 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
   const int grid = (int)(ngroups < sms ? ngroups : sms);
   const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
   estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
-                                                                   h | (h << 16), h, margin, q, ldq, err);
+                                                                   h | (h << 16), h, margin, mma_mode, q, ldq, cmask, sbase_hint, err);
   return cudaGetLastError();
 }
 
-cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, double* Fz) {
+cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
+                           double* Fz) {
   if (N <= 0) return cudaSuccess;
   if (K > 256 || (ldq & 3)) return cudaErrorInvalidValue;
-  const int64_t want = (N + 31) / 32;  // 8 warps x 4 rows per CTA pass
-  const int grid = (int)(want < (int64_t)sms * 8 ? want : (int64_t)sms * 8);
-  estep_finalize_kernel<<<grid, 256, 0, st>>>(q, ldq, N, K, Fz);
+  const int W = (K + 31) / 32;
+  const int grid = sms * 16;
+  if (K <= 32) estep_finalize_kernel<8, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else if (K <= 64) estep_finalize_kernel<16, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else if (K <= 128) estep_finalize_kernel<32, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else estep_finalize_kernel<32, 2><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  return cudaGetLastError();
+}
+
+cudaError_t apply_candidate_mask(cudaStream_t st, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask) {
+  if (N <= 0) return cudaSuccess;
+  const int64_t total = N * K;
+  apply_mask_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(q, ldq, N, K, cmask, (K + 31) / 32);
+  return cudaGetLastError();
+}
+
+cudaError_t mask_count(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockcnt) {
+  if (N <= 0) return cudaSuccess;
+  mask_lists_kernel<false><<<(unsigned)((N + kMaskBlock - 1) / kMaskBlock), 256, sizeof(int) * K, st>>>(
+      cmask, (K + 31) / 32, N, K, blockcnt, nullptr, nullptr);
+  return cudaGetLastError();
+}
+
+cudaError_t mask_fill(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockoff, const long long* koff,
+                      int32_t* lrow) {
+  if (N <= 0) return cudaSuccess;
+  mask_lists_kernel<true><<<(unsigned)((N + kMaskBlock - 1) / kMaskBlock), 256, sizeof(int) * K, st>>>(
+      cmask, (K + 31) / 32, N, K, blockoff, koff, lrow);
+  return cudaGetLastError();
+}
+
+cudaError_t gather_list_q(cudaStream_t st, int sms, const float* q, int64_t ldq, const int32_t* lrow,
+                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk) {
+  if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  long long bx = (maxcnt + 255) / 256;
+  const long long cap = std::max<long long>(1, (long long)sms * 8 / K);
+  if (bx > cap) bx = cap;
+  gather_list_q_kernel<<<dim3((unsigned)bx, (unsigned)K), 256, 0, st>>>(q, ldq, lrow, koff, kcnt, lq, Nk);
   return cudaGetLastError();
 }
 

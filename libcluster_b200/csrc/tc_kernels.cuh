@@ -17,23 +17,37 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err);
 
 // ---- two-level E step ------------------------------------------------------------------
-// level 1: one-product distances with a rigorous error bound; q[n][k] = upper bound of the logit for candidate
-//          pairs, -inf for pairs that cannot reach e^-margin of the row's best.  cpar [4][K] = {1/(s_g tau_k)^2,
-//          Ek, Ea, chat}; augblob = ceil(K/4) blocks of kTcAugBlockBytes (tc_pack_aug); aug_exp = P (A slot = 2^P)
+// level 1: one-product distances with a rigorous error bound.  q[n][k] = upper bound of the logit; cmask [N][W],
+//          W = ceil(K / 32): bit k of row n set iff the pair can reach e^-margin of the row's best (a *candidate*).
+//          cpar [4][K] = {1/(s_g tau_k)^2, Ek, Ea, chat}; augblob = ceil(K/4) blocks of kTcAugBlockBytes
+//          (tc_pack_aug); aug_exp = P (A slot = 2^P); mma_mode: issue order of the MMAs (tc_kernels.cu, kMma*)
 constexpr uint32_t kTcAugBlockBytes = 16384;
 constexpr int kTcCoarseMaxK = 256;
 cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
-                               float margin, float* q, int64_t ldq, unsigned* err);
-// level 2: exact logits of the candidate pairs (per-cluster row lists as built by nz_count/nz_scan/nz_fill with
-//          pred = kNzNotNegInf; itoff [K+1] = prefix of ceil(kcnt[k] / 128)), written into q[row][k]
+                               float margin, int mma_mode, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
+                               unsigned* err);
+// err[1] of a launch whose sbase_hint did not match: 0x80000000 | the 1024-aligned shared-memory base to pass instead
+constexpr uint32_t kTcSbaseDefault = 1024;
+// candidate masks -> per-cluster row lists: mask_count, nz_scan (kernels.cuh), mask_fill
+cudaError_t mask_count(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockcnt);
+cudaError_t mask_fill(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockoff, const long long* koff,
+                      int32_t* lrow);
+// level 2: exact logits of the candidate pairs, written into q[row][k].  itoff [K+1] = prefix of
+//          ceil(kcnt[k] / 128); items = scratch of 16 bytes per 128-pair work item
 cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                              const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                              const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
-                             const int32_t* itoff, int64_t nitems, float* q, int64_t ldq, unsigned* err);
-// level 3: q = softmax over the logits in q (-inf -> 0), Fz += sum log Z
-cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, double* Fz);
+                             const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err);
+// level 3: q = softmax over the candidate logits (0 elsewhere), Fz += sum log Z
+cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
+                           double* Fz);
+// q = -inf outside the candidate mask (test modes only)
+cudaError_t apply_candidate_mask(cudaStream_t st, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask);
+// lq[e] = q[lrow[e]][k] over the lists, Nk[k] += sum: lets the statistics pass reuse the candidate lists
+cudaError_t gather_list_q(cudaStream_t st, int sms, const float* q, int64_t ldq, const int32_t* lrow,
+                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk);
 cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out);
 double tc_pack_aug(const double* w, int k, uint8_t* augblob);
 
