@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <thread>
 
 #include "kernels.cuh"
 #include "tc_kernels.cuh"
@@ -97,8 +98,12 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   if (const char* tl = std::getenv("LCB_TC_TWO_LEVEL")) {
     if (tl[0]) use_two_level_ = tl[0] != '0';
   }
-  if (const char* mm = std::getenv("LCB_TC_MMA_MODE")) {
-    if (mm[0] >= '0' && mm[0] <= '2') tc_mma_mode_ = mm[0] - '0';
+  // host threads of the O(K D^3) posterior updates: the machine's cores (not OMP_NUM_THREADS, which launchers often
+  // pin to 1 for unrelated reasons); LCB_HOST_THREADS overrides
+  host_threads_ = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  if (const char* ht = std::getenv("LCB_HOST_THREADS")) {
+    const int n = std::atoi(ht);
+    if (n >= 1 && n <= 1024) host_threads_ = n;
   }
   if (const char* sg = std::getenv("LCB_TC_STAGE")) {
     if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
@@ -316,11 +321,26 @@ void Engine::upload_rows(View& v, const double* const* X, const int64_t* Nj, con
 void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int D, const int64_t* ld, int layout) {
   if (J < 1 || D < 1 || X == nullptr || Nj == nullptr) throw_invalid("set_data: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
-  free_view(main_);
   int64_t N = 0;
   for (int j = 0; j < J; ++j) {
     if (Nj[j] < 0 || (Nj[j] > 0 && X[j] == nullptr)) throw_invalid("set_data: bad group");
     N += Nj[j];
+  }
+  // A matrix of the shape of the resident one (batches streamed through one engine) reuses its device buffers:
+  // cudaFree + cudaMalloc of tens of GB cost more than 100 ms, a tenth of the upload itself.
+  View keep;
+  if (main_.owns_x && main_.X && J == 1 && main_.J == 1 && main_.N == N && main_.D == D && N > 0) {
+    keep = main_;
+    if (keep.xnorm) cudaFree(keep.xnorm);  // row norms belong to the old rows
+    main_ = View();
+    main_.X = keep.X;
+    main_.q = keep.q;
+    main_.q2 = keep.q2;
+    main_.ldq = keep.ldq;
+    main_.owns_x = true;
+    list_valid_ = false;
+  } else {
+    free_view(main_);
   }
   Nj_.assign(Nj, Nj + J);
   // Centre subtracted at upload: the column mean of (at most) the first 2^20
@@ -333,10 +353,18 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
       const int64_t ldj = ld ? ld[j] : (layout == 0 ? D : Nj[j]);
       const int64_t take = std::min(left, Nj[j]);
       if (layout == 0) {
-        for (int64_t n = 0; n < take; ++n) {
-          const double* row = X[j] + n * ldj;
-          for (int d = 0; d < D; ++d) sums[d] += row[d];
+        const int nb = (int)std::min<int64_t>(64, (take + 4095) / 4096);
+        std::vector<double> part((size_t)nb * D, 0.0);
+#pragma omp parallel for schedule(static) num_threads(host_threads_)
+        for (int b = 0; b < nb; ++b) {
+          double* ps = part.data() + (size_t)b * D;
+          for (int64_t n = take * b / nb; n < take * (b + 1) / nb; ++n) {
+            const double* row = X[j] + n * ldj;
+            for (int d = 0; d < D; ++d) ps[d] += row[d];
+          }
         }
+        for (int b = 0; b < nb; ++b)
+          for (int d = 0; d < D; ++d) sums[d] += part[(size_t)b * D + d];
       } else {
         for (int d = 0; d < D; ++d) {
           double s = 0;
@@ -362,7 +390,7 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
   main_.ldx = round_up(D, 4);
   main_.owns_x = true;
   const size_t es = prec_ == kF32 ? 4 : 8;
-  dev_alloc(&main_.X, (size_t)std::max<int64_t>(N, 1) * main_.ldx * es);
+  if (main_.X == nullptr) dev_alloc(&main_.X, (size_t)std::max<int64_t>(N, 1) * main_.ldx * es);
   if (J > 1) {
     dev_alloc((void**)&main_.gid, sizeof(int32_t) * std::max<int64_t>(N, 1));
     std::vector<int32_t> g((size_t)N);
@@ -636,7 +664,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   const double* xs = Njk + nJK;
   const double* S = xs + (int64_t)K * D;
   for (int j = 0; j < J; ++j) weights[j].update(Njk + (int64_t)j * K, K);
-#pragma omp parallel for schedule(dynamic) if (K >= 8)
+#pragma omp parallel for schedule(dynamic) num_threads(host_threads_) if (K >= 8)
   for (int k = 0; k < K; ++k) {
     double n = 0;
     for (int j = 0; j < J; ++j)
@@ -781,7 +809,7 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   const double sg = std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(256.0 / xspan)))));
   std::vector<double> vaug(try_two ? (size_t)K * D : 0), tau(K), rfro(K);
   double vmax = 0;
-#pragma omp parallel for schedule(dynamic) reduction(max : vmax) if (K >= 8)
+#pragma omp parallel for schedule(dynamic) reduction(max : vmax) num_threads(host_threads_) if (K >= 8)
   for (int k = 0; k < K; ++k) {
     std::vector<double> R;
     clusters[k].whitener(R);
@@ -913,7 +941,7 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
   for (int attempt = 0;; ++attempt) {
     check(cudaEventRecord(ev_[4], stream_), "event");
     check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
-                                  d_act, sg, aug_exp, kMargin, tc_mma_mode_, q, v.ldq, cmask, coarse_sbase_hint_, d_err),
+                                  d_act, sg, aug_exp, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, d_err),
           "estep_coarse_tc128 launch");
     ++launches_;
     check(cudaEventRecord(ev_[5], stream_), "event");
@@ -1039,7 +1067,7 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
   {
     int bad = 0;
     Error first{0, ""};
-#pragma omp parallel for schedule(dynamic) if (K >= 8)
+#pragma omp parallel for schedule(dynamic) num_threads(host_threads_) if (K >= 8)
     for (int k = 0; k < K; ++k) {
       try {
         clusters[k].update();
@@ -1057,7 +1085,7 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
   double Fw = 0, Fc = 0;
   for (size_t j = 0; j < weights.size(); ++j) Fw += weights[j].fenergy();
   std::vector<double> fck(K);
-#pragma omp parallel for schedule(dynamic) if (K >= 8)
+#pragma omp parallel for schedule(dynamic) num_threads(host_threads_) if (K >= 8)
   for (int k = 0; k < K; ++k) fck[k] = clusters[k].fenergy();
   for (int k = 0; k < K; ++k) Fc += fck[k];
   *F = Fc + Fw + Fz;

@@ -112,8 +112,8 @@ class Engine {
   // Two-level E step (one-product distances for all pairs, exact logits for the candidates only).
   // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
   bool use_two_level_ = true;
+  int host_threads_ = 1;        // threads of the host-side posterior updates (engine.cu)
   int tc_stage_ = 0;            // 0 full, 1 stop after level 1, 2 stop after level 2
-  int tc_mma_mode_ = 0;         // MMA issue order of level 1 (tc_kernels.cu: kMma*); LCB_TC_MMA_MODE overrides
   int two_level_skip_ = 0;      // iterations left before the two-level path is tried again after it did not pay
   uint32_t coarse_sbase_hint_ = 1024;  // shared-memory base the level-1 kernel takes as a parameter (tc_kernels.cuh)
   bool coarse_hint_ok_ = false;

@@ -813,12 +813,6 @@ constexpr uint32_t kCOffLb = kCOffPar + 4 * 256 * 4;           // 208896: [2 par
 constexpr uint32_t kCOffBar = kCOffLb + 2 * 2 * kCRows * 4;    // 215040
 constexpr uint32_t kCSmemBytes = kCOffBar + 512 + 1024;
 constexpr uint32_t kCAcol = 72;                                // TMEM columns of one A slot
-// Order and shapes of the MMAs of one (cluster, tile) item.  R_k is lower-triangular, so the K chunk of input
-// dimensions [16c, 16c+16) only feeds output columns >= 16c.
-//   kMmaShrink8    eight chunks with N = 128 - 16c: least tensor work (4.5 full-width MMAs), eight changes of shape
-//   kMmaTwoShapes  chunks 0-3 at N = 128, chunks 4-7 at N = 64: 6 full-width MMAs, two shapes
-//   kMmaSplitHalves columns [0,64) and [64,128) as two independent accumulate chains, issued alternately
-enum { kMmaShrink8 = 0, kMmaTwoShapes = 1, kMmaSplitHalves = 2 };
 enum {
   CB_FULL0 = 0, CB_EMPTY0 = 3, CG_FULL0 = 6, CG_EMPTY0 = 8, CA_READY0 = 10, CA_FREE0 = 13, CT_FULL0 = 16, CT_EMPTY0 = 18,
   CL_FULL0 = 20, CL_FREE0 = 22, C_COUNT = 24
@@ -847,11 +841,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
                "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
-// sum of squares of 64 fp32 register values with packed FMAs, four independent chains
-__device__ __forceinline__ float sumsq64(const uint32_t* r) {
+// sum of squares of 128 fp32 register values: eight independent chains of packed FMAs, packed adds to fold them
+__device__ __forceinline__ float sumsq128(const uint32_t* r) {
   unsigned long long acc[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-  for (int i = 0; i < 64; i += 16) {
+  for (int i = 0; i < 128; i += 16) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       unsigned long long p;
@@ -859,17 +853,112 @@ __device__ __forceinline__ float sumsq64(const uint32_t* r) {
       asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc[c]) : "l"(p));
     }
   }
-  float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint32_t a, b;
-    asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(acc[c]));
-    s += __uint_as_float(a) + __uint_as_float(b);
+  for (int h = 4; h >= 1; h >>= 1) {
+#pragma unroll
+    for (int c = 0; c < h; ++c) asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc[c]) : "l"(acc[c + h]));
   }
-  return s;
+  uint32_t a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(acc[0]));
+  return __uint_as_float(a) + __uint_as_float(b);
 }
 __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+// ---------------------------------------------------------------- MMA issuers of the level-1 kernel --
+// Three issuing warps, one per tile slot S of the group; item (k, S) is the ic-th item of this CTA,
+// ic = 3 (K g + k) + S, and uses accumulator ic & 1.  One issuer needs ~850 cycles of dependent uniform-datapath
+// instructions per item (waits, descriptor arithmetic, nine MMAs, commits) against ~370 tensor cycles: a single
+// issuer left the tensor pipe 57 % idle, two issuers 33 % (profiles/ncu_r01_coarse_v2_raw.csv, ..._v3_raw.csv).
+// Shared-memory addresses derive from the kernel parameter sbase_hint and the loop counters only (TMEM base = 0: the
+// CTA owns all 512 columns), which keeps the loop on the uniform datapath.
+template <uint32_t S>
+__device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ngroups, unsigned* err) {
+  constexpr uint32_t a0 = 256u + kCAcol * S;
+  const uint32_t barb = sb + kCOffBar;
+  const uint32_t blo_base = umma_desc_lo(sb), glo_base = umma_desc_lo(sb + kCOffAug);
+  uint32_t ic = S, gcnt = 0, acnt = 0;
+  uint32_t bs = 0, bph = 0, as = 0;
+  for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
+    mbar_wait(barb + 8u * (CA_READY0 + S), gcnt & 1, err);
+    for (int k = 0; k < K; ++k, ic += 3) {
+      if ((k & 3) == 0) {
+        as = acnt & 1;
+        mbar_wait(barb + 8u * (CG_FULL0 + as), (acnt >> 1) & 1, err);
+        ++acnt;
+      }
+      mbar_wait(barb + 8u * (CB_FULL0 + bs), bph, err);
+      const uint32_t lo0 = blo_base + bs * (kCBStage >> 4), lo1 = lo0 + (16384u >> 4);
+      const uint32_t log_ = glo_base + as * (kTcAugBlockBytes >> 4) + 2u * (uint32_t)(k & 3);
+      const uint32_t acc = ic & 1u;
+      const bool last = k == K - 1, aug_done = (k & 3) == 3 || last;
+      if (elect_one()) {
+        // One asm block: wait until the epilogue has drained the accumulator -- the previous ic >> 1 items that used
+        // it, four arrivals each, counted in shared memory: the three issuers take turns on an accumulator, and a
+        // phase-parity wait cannot tell "the item before the previous one is still being drained" from "the
+        // previous one has been drained" --, then
+        //   accumulator = -s_g tau_k R_k m_k (aug chunk, K = 16), followed by the eight triangular chunks (R_k is
+        //   lower-triangular, so the K chunk of input dimensions [16c, 16c+16) only feeds output columns >= 16c:
+        //   N = 128 - 16c), and the commit.
+        // Instruction descriptors: D = f32, A = B = f16, K-major, M = 128, N as above.  The spin is bounded: a
+        // protocol bug traps instead of hanging the device.
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q, r;\n\t"
+            ".reg .b64 bd;\n\t"
+            ".reg .b32 t, c;\n\t"
+            "setp.ne.b32 p, 1, 0;\n\t"
+            "mov.u32 c, 0;\n\t"
+            "CW_WAIT_%=:\n\t"
+            "add.u32 c, c, 1;\n\t"
+            "setp.gt.u32 r, c, 67108864;\n\t"
+            "@r trap;\n\t"
+            "ld.acquire.cta.shared.u32 t, [%0];\n\t"
+            "sub.u32 t, t, %1;\n\t"
+            "setp.lt.s32 q, t, 0;\n\t"
+            "@q bra CW_WAIT_%=;\n\t"
+            "tcgen05.fence::after_thread_sync;\n\t"
+            "mov.b64 bd, {%6, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3+64], bd, 0x8200010, !p;\n\t"
+            "mov.b64 bd, {%4, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], bd, 0x8200010, p;\n\t"
+            "add.u32 t, %4, 0x82;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+16], [%3+8], bd, 0x81c0010, p;\n\t"
+            "add.u32 t, %4, 0x104;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+32], [%3+16], bd, 0x8180010, p;\n\t"
+            "add.u32 t, %4, 0x186;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+48], [%3+24], bd, 0x8140010, p;\n\t"
+            "mov.b64 bd, {%5, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+32], bd, 0x8100010, p;\n\t"
+            "add.u32 t, %5, 0x82;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+80], [%3+40], bd, 0x80c0010, p;\n\t"
+            "add.u32 t, %5, 0x104;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+96], [%3+48], bd, 0x8080010, p;\n\t"
+            "add.u32 t, %5, 0x186;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+112], [%3+56], bd, 0x8040010, p;\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+            "}"
+            ::"r"(barb + 8u * C_COUNT + 16u + 4u * acc), "r"(4u * (ic >> 1)), "r"(128u * acc), "r"(a0), "r"(lo0), "r"(lo1),
+              "r"(log_), "r"(kDescHi), "r"(barb + 8u * (CT_FULL0 + acc)), "r"(barb + 8u * (CB_EMPTY0 + bs))
+            : "memory");
+        if (aug_done) tc_commit(barb + 8u * (CG_EMPTY0 + as));
+        if (last) tc_commit(barb + 8u * (CA_FREE0 + S));
+      }
+      __syncwarp();
+      if (++bs == kCStages) {
+        bs = 0;
+        bph ^= 1;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(kThreadsTc, 1)
@@ -877,7 +966,7 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
                           const int32_t* __restrict__ gid, int K, const uint8_t* __restrict__ blob,
                           const uint8_t* __restrict__ augblob, const float* __restrict__ cpar /* [4][K] */,
                           const float* __restrict__ lw, const uint8_t* __restrict__ act, float sg, uint32_t aug01,
-                          uint32_t aug2, float margin, int mma_mode, float* __restrict__ q, int64_t ldq,
+                          uint32_t aug2, float margin, float* __restrict__ q, int64_t ldq,
                           uint32_t* __restrict__ cmask, uint32_t sbase_hint, unsigned* __restrict__ err) {
   extern __shared__ unsigned char smem_dyn[];
   // opaque copies: the compiler would otherwise rematerialise these from special registers (S2R / S2UR, ~50 cycles
@@ -906,19 +995,21 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
   if (tid == 0) {
     for (int i = 0; i < kCStages; ++i) {
       mbar_init(bar(CB_FULL0 + i), 1);
-      mbar_init(bar(CB_EMPTY0 + i), 1);
+      mbar_init(bar(CB_EMPTY0 + i), 3);  // the three MMA issuers
       mbar_init(bar(CA_READY0 + i), 4);  // 4 stager warps (lane quadrants)
-      mbar_init(bar(CA_FREE0 + i), 1);
+      mbar_init(bar(CA_FREE0 + i), 1);   // the issuer of tile slot i
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(bar(CG_FULL0 + i), 1);
-      mbar_init(bar(CG_EMPTY0 + i), 1);
+      mbar_init(bar(CG_EMPTY0 + i), 3);  // the three MMA issuers
       mbar_init(bar(CT_FULL0 + i), 1);
-      mbar_init(bar(CT_EMPTY0 + i), 4);  // 4 warps of the epilogue group
       mbar_init(bar(CL_FULL0 + i), 8);   // 8 epilogue warps
       mbar_init(bar(CL_FREE0 + i), 4);   // 4 stager warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // drained-items counters of the two accumulators (4 arrivals per item), behind the TMEM slot
+    reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT + 16)[0] = 0u;
+    reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT + 16)[1] = 0u;
   }
   for (int i = (int)tid; i < 4 * 256; i += kThreadsTc) {
     const int a = i >> 8, k = i & 255;
@@ -967,82 +1058,9 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
         }
       }
     }
-    if (warp == 1) {
-      // -------------------------------------------------------- MMA issuer --
-      // Every address below derives from kernel parameters, constants and the loop counters only (TMEM base = 0:
-      // this CTA owns all 512 columns; shared-memory base = sbase_hint), so the whole loop runs on the uniform
-      // datapath; the first version spent ~900 cycles per item moving values from vector to uniform registers.
-      const uint32_t sb = sbase_hint;
-      const uint32_t barb = sb + kCOffBar;
-      uint32_t icnt = 0, gcnt = 0, acnt = 0;
-      uint32_t bs = 0, bph = 0, as = 0;
-      for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
-        for (int k = 0; k < K; ++k) {
-          if ((k & 3) == 0) {
-            as = acnt & 1;
-            mbar_wait(barb + 8u * (CG_FULL0 + as), (acnt >> 1) & 1, err);
-            ++acnt;
-          }
-          mbar_wait(barb + 8u * (CB_FULL0 + bs), bph, err);
-          const uint32_t lo0 = umma_desc_lo(sb + bs * kCBStage), lo1 = lo0 + (16384u >> 4);
-          const uint32_t log_ = umma_desc_lo(sb + kCOffAug + as * kTcAugBlockBytes) + 2u * (uint32_t)(k & 3);
-          const bool last_k = k == K - 1;
-#pragma unroll
-          for (int s = 0; s < kCT; ++s, ++icnt) {
-            const uint32_t a = icnt & 1, ph = (icnt >> 1) & 1;
-            if (k == 0) mbar_wait(barb + 8u * (CA_READY0 + s), gcnt & 1, err);
-            mbar_wait(barb + 8u * (CT_EMPTY0 + a), ph ^ 1, err);
-            tc_fence_after();
-            const uint32_t d0 = 128u * a;
-            const uint32_t a0 = 256u + kCAcol * (uint32_t)s;
-            if (elect_one()) {
-              // accumulator = -s_g tau_k R_k m_k (aug chunk), then the triangular chunks; see kMma* above
-              tc_mma_f16_ts_w(d0, a0 + 64u, log_, kDescHi, umma_idesc(128), 0u);
-              if (mma_mode == kMmaShrink8) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const int kb = c >> 2, c4 = c & 3;
-                  const uint32_t off = (uint32_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
-                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, (kb ? lo1 : lo0) + off, kDescHi, umma_idesc(128 - 16 * c), 1u);
-                }
-              } else if (mma_mode == kMmaTwoShapes) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const int kb = c >> 2, c4 = c & 3;
-                  tc_mma_f16_ts_w(d0 + 64 * kb, a0 + 8 * c, (kb ? lo1 : lo0) + (uint32_t)((32 * c4) >> 4), kDescHi,
-                                  umma_idesc(128 - 64 * kb), 1u);
-                }
-              } else {
-                // columns [0,64) and [64,128) are independent accumulators: alternate between them
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                  tc_mma_f16_ts_w(d0 + 64, a0 + 8 * c, lo0 + (uint32_t)((64 * 128 + 32 * c) >> 4), kDescHi, umma_idesc(64), 1u);
-                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, lo0 + (uint32_t)((16 * c * 128 + 32 * c) >> 4), kDescHi,
-                                  umma_idesc(64 - 16 * c), 1u);
-                }
-#pragma unroll
-                for (int c = 4; c < 8; ++c)
-                  tc_mma_f16_ts_w(d0 + 16 * c, a0 + 8 * c, lo1 + (uint32_t)(((16 * c - 64) * 128 + 32 * (c - 4)) >> 4), kDescHi,
-                                  umma_idesc(128 - 16 * c), 1u);
-              }
-              tc_commit(barb + 8u * (CT_FULL0 + a));
-              if (last_k) tc_commit(barb + 8u * (CA_FREE0 + s));
-            }
-            __syncwarp();
-          }
-          const bool aug_done = (k & 3) == 3 || last_k;
-          if (elect_one()) {
-            tc_commit(barb + 8u * (CB_EMPTY0 + bs));
-            if (aug_done) tc_commit(barb + 8u * (CG_EMPTY0 + as));
-          }
-          __syncwarp();
-          if (++bs == kCStages) {
-            bs = 0;
-            bph ^= 1;
-          }
-        }
-      }
-    }
+    if (warp == 1) coarse_mma_issuer<0>(sbase_hint, K, ngroups, err);
+    if (warp == 2) coarse_mma_issuer<1>(sbase_hint, K, ngroups, err);
+    if (warp == 3) coarse_mma_issuer<2>(sbase_hint, K, ngroups, err);
   } else if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // --------------------------------------------------------------- stagers --
@@ -1168,8 +1186,10 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     // -------------------------------------------------------------- epilogue --
     const int grp = (warp - 8) >> 2, quad = warp & 3;
     const uint32_t tacc = tmem_base + ((uint32_t)(32 * quad) << 16) + 128u * (uint32_t)grp;
-    const uint32_t bfull = bar(CT_FULL0 + grp), bempty = bar(CT_EMPTY0 + grp);
+    const uint32_t bfull = bar(CT_FULL0 + grp), drained = sBar + 8u * C_COUNT + 16u + 4u * (uint32_t)grp;
     const bool grouped = gid != nullptr;
+    const bool special = grouped || act != nullptr;  // per-row weights or an active mask: the rare, slower tail
+    const uint32_t spar_s = sbase + kCOffPar;
     uint32_t icnt = 0, gcnt = 0;
     for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
       float* qrow[kCT];
@@ -1189,14 +1209,22 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       }
 #pragma unroll 1
       for (int k = 0; k < K; ++k) {
-        const float cinv2 = spar[k], ek = spar[256 + k], ea = spar[512 + k], ch = spar[768 + k];
+        float cinv2, ek, ea, ch;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cinv2) : "r"(spar_s + 4u * (uint32_t)k));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ek) : "r"(spar_s + 4u * (uint32_t)k + 1024u));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ea) : "r"(spar_s + 4u * (uint32_t)k + 2048u));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ch) : "r"(spar_s + 4u * (uint32_t)k + 3072u));
 #pragma unroll
         for (int s = 0; s < kCT; ++s, ++icnt) {
+          // the icnt-th item of this CTA lives in accumulator icnt & 1 (see the MMA issuers)
           if ((int)(icnt & 1) != grp) continue;
           // everything that does not depend on the accumulator first: its latency hides behind the wait
           float c = ch;
-          if (grouped) c += __ldg(lwg[s] + k);
-          const bool off = actg[s] != nullptr && !__ldg(actg[s] + k);
+          bool off = false;
+          if (special) {
+            if (grouped) c += __ldg(lwg[s] + k);
+            off = actg[s] != nullptr && !__ldg(actg[s] + k);
+          }
           const float e = fmaf(ek, xn[s], ea);
           mbar_wait(bfull, (icnt >> 1) & 1, err);
           tc_fence_after();
@@ -1206,11 +1234,11 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bempty);
-          const float ss = sumsq64(r) + sumsq64(r + 64);
+          if (lane == 0) asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(drained) : "memory");
+          const float ss = sumsq128(r);
           if (qrow[s] != nullptr) {
             float d;
-            asm("sqrt.approx.f32 %0, %1;" : "=f"(d) : "f"(ss * cinv2));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(ss * cinv2));
             const float dlo = fmaxf(d - e, 0.f), dhi = d + e;
             float ub = fmaf(-0.5f * dlo, dlo, c), lb = fmaf(-0.5f * dhi, dhi, c);
             ub += 2e-6f * fabsf(ub) + 1e-3f;   // fp32 rounding of the bound itself (approximate square root)
@@ -1263,13 +1291,18 @@ estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, cons
 #pragma unroll
       for (int j = 0; j < NV; ++j) {
         const int k = 4 * sub + 4 * LPR * j;
-        if (n < N && k < K) {
-          v[u][j] = *reinterpret_cast<const float4*>(q + n * ldq + k);
-          m[u][j] = (__ldg(cmask + n * W + (k >> 5)) >> (k & 31)) & 0xFu;
-        } else {
-          v[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          m[u][j] = 0u;
-        }
+        m[u][j] = (n < N && k < K) ? (__ldg(cmask + n * W + (k >> 5)) >> (k & 31)) & 0xFu : 0u;
+      }
+    }
+    // only the 16-byte groups that hold a candidate are read: q is otherwise write-only here (the non-candidate
+    // entries still hold level-1 bounds nobody needs), which halves the HBM traffic of the pass
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t n = r0 + u * RPW + rsel;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int k = 4 * sub + 4 * LPR * j;
+        v[u][j] = m[u][j] ? *reinterpret_cast<const float4*>(q + n * ldq + k) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -1444,7 +1477,7 @@ cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N
 cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
-                               float margin, int mma_mode, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
+                               float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
                                unsigned* err) {
   if (N <= 0) return cudaSuccess;
   if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
@@ -1454,7 +1487,7 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
   const int grid = (int)(ngroups < sms ? ngroups : sms);
   const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
   estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
-                                                                   h | (h << 16), h, margin, mma_mode, q, ldq, cmask, sbase_hint, err);
+                                                                   h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, err);
   return cudaGetLastError();
 }
 

@@ -20,13 +20,13 @@ cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, con
 // level 1: one-product distances with a rigorous error bound.  q[n][k] = upper bound of the logit; cmask [N][W],
 //          W = ceil(K / 32): bit k of row n set iff the pair can reach e^-margin of the row's best (a *candidate*).
 //          cpar [4][K] = {1/(s_g tau_k)^2, Ek, Ea, chat}; augblob = ceil(K/4) blocks of kTcAugBlockBytes
-//          (tc_pack_aug); aug_exp = P (A slot = 2^P); mma_mode: issue order of the MMAs (tc_kernels.cu, kMma*)
+//          (tc_pack_aug); aug_exp = P (A slot = 2^P)
 constexpr uint32_t kTcAugBlockBytes = 16384;
 constexpr int kTcCoarseMaxK = 256;
 cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const float* xnorm, int64_t N,
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
-                               float margin, int mma_mode, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
+                               float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
                                unsigned* err);
 // err[1] of a launch whose sbase_hint did not match: 0x80000000 | the 1024-aligned shared-memory base to pass instead
 constexpr uint32_t kTcSbaseDefault = 1024;

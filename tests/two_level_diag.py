@@ -21,18 +21,15 @@ from conftest import make_blobs, soft_labels  # noqa: E402
 D = 128
 
 
-def engine(two_level, stage=None, prec=lc.F32, mma_mode=None):
+def engine(two_level, stage=None, prec=lc.F32):
     os.environ["LCB_TC_TWO_LEVEL"] = "1" if two_level else "0"
     if stage:
         os.environ["LCB_TC_STAGE"] = stage
-    if mma_mode is not None:
-        os.environ["LCB_TC_MMA_MODE"] = str(mma_mode)
     try:
         return lc.Engine(0, prec)
     finally:
         os.environ.pop("LCB_TC_TWO_LEVEL", None)
         os.environ.pop("LCB_TC_STAGE", None)
-        os.environ.pop("LCB_TC_MMA_MODE", None)
 
 
 def run(X, q0, **kw):
@@ -98,8 +95,8 @@ def big(N=4_000_000, K=64):
         X[idx] = mu[k] + torch.randn(idx.numel(), D, device=dev, generator=g) @ Lc[k].T
     torch.cuda.synchronize()
     res = {}
-    for two, mode in ((False, None), (True, 0), (True, 1), (True, 2)):
-        eng = engine(two, mma_mode=mode)
+    for two in (False, True):
+        eng = engine(two)
         eng.set_data_device(X.data_ptr(), N, D, D)
         eng.model_init(lc.BGMM)
         eng.set_labels_device(z.data_ptr(), K)
@@ -109,13 +106,13 @@ def big(N=4_000_000, K=64):
             Fs.append(eng.vbem_step())
             dt = time.perf_counter() - t0
             t, d = eng.step_timing(), eng.estep_detail()
-            print("two_level=%s mma_mode=%s step %d: F=%.10g wall %.1f ms | S %.2f E %.2f step %.2f launches %d | "
+            print("two_level=%s step %d: F=%.10g wall %.1f ms | S %.2f E %.2f step %.2f launches %d | "
                   "coarse %.3f lists %.3f refine %.3f finalize %.3f pairs %d path %d" % (
-                      two, mode, i, Fs[-1], dt * 1e3, t["sstat_ms"], t["estep_ms"], t["step_ms"], t["launches"],
+                      two, i, Fs[-1], dt * 1e3, t["sstat_ms"], t["estep_ms"], t["step_ms"], t["launches"],
                       d["coarse_ms"], d["lists_ms"], d["refine_ms"], d["finalize_ms"], d["pairs"], d["path"]), flush=True)
-        res[(two, mode)] = Fs
+        res[two] = Fs
         eng.close()
-    base = res[(False, None)]
+    base = res[False]
     for key, Fs in res.items():
         print(key, "F", Fs, "rel diff vs dense", [abs(a - b) / abs(a) for a, b in zip(base, Fs)], flush=True)
 
