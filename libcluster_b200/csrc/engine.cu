@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -318,6 +319,106 @@ void Engine::upload_rows(View& v, const double* const* X, const int64_t* Nj, con
   cleanup();
 }
 
+// fp32 engine, row-major groups.  The link is the bottleneck of an upload (51 GB of fp64 for the 50M x 128 case), so
+// the host's threads turn the rows into centred fp32 in page-locked staging and only those 4 bytes per value cross
+// PCIe, straight to their final place in X.  The conversions rarely keep the link busy on their own; when the
+// caller's buffer is page-locked, a second lane sends raw fp64 blocks from the other end of the group (converted by
+// convert_rows on the device), each sized to fill the link time the last conversion left idle.  Both lanes produce
+// (float)(x - mean) with the subtraction in fp64, so the resident X does not depend on the split.
+void Engine::upload_rows_f32(View& v, const double* const* X, const int64_t* Nj, const int64_t* ld, int J,
+                             const std::vector<double>& mean) {
+  const int D = v.D;
+  const int64_t ldx = v.ldx;
+  constexpr double kLinkBytesPerSec = 50e9;  // page-locked H2D rate assumed when sizing the raw blocks
+  constexpr int kSlots = 3;
+  const int64_t crow = std::max<int64_t>(1, (int64_t)(16u << 20) / (4 * ldx));
+  const size_t slot_floats = (size_t)crow * ldx;
+  struct Res {
+    cudaStream_t s32 = nullptr, sraw = nullptr;
+    cudaEvent_t e32[kSlots] = {nullptr, nullptr, nullptr}, eraw[2] = {nullptr, nullptr};
+    void* dstage[2] = {nullptr, nullptr};
+    ~Res() {
+      if (s32) cudaStreamSynchronize(s32);
+      if (sraw) cudaStreamSynchronize(sraw);
+      for (cudaEvent_t e : e32) if (e) cudaEventDestroy(e);
+      for (cudaEvent_t e : eraw) if (e) cudaEventDestroy(e);
+      for (void* p : dstage) if (p) cudaFree(p);
+      if (s32) cudaStreamDestroy(s32);
+      if (sraw) cudaStreamDestroy(sraw);
+    }
+  } r;
+  float* hslot = (float*)pinned(kSlots * slot_floats * sizeof(float));
+  reserve(d_mean_, sizeof(double) * D);
+  double* d_mean = (double*)d_mean_.p;
+  check(cudaMemcpyAsync(d_mean, mean.data(), sizeof(double) * D, cudaMemcpyHostToDevice, stream_), "H2D mean");
+  sync();
+  check(cudaStreamCreateWithFlags(&r.s32, cudaStreamNonBlocking), "stream");
+  check(cudaStreamCreateWithFlags(&r.sraw, cudaStreamNonBlocking), "stream");
+  for (int i = 0; i < kSlots; ++i) check(cudaEventCreateWithFlags(&r.e32[i], cudaEventDisableTiming), "event");
+  for (int i = 0; i < 2; ++i) check(cudaEventCreateWithFlags(&r.eraw[i], cudaEventDisableTiming), "event");
+  bool used32[kSlots] = {false, false, false}, usedraw[2] = {false, false};
+  int slot = 0, rslot = 0;
+  const double* mu = mean.data();
+  int64_t row0 = 0;
+  for (int j = 0; j < J; ++j) {
+    const int64_t n = Nj[j];
+    const int64_t ldj = ld ? ld[j] : D;
+    bool pinned_src = false;
+    if (n > 0 && ldj == D) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, X[j]) == cudaSuccess) pinned_src = at.type == cudaMemoryTypeHost;
+      else cudaGetLastError();
+    }
+    int64_t front = 0, back = n;  // rows [front, back) of the group are still to be sent
+    while (front < back) {
+      // ---- fp32 lane: the block at the back of what is left ----
+      const int64_t rows = std::min(crow, back - front), b0 = back - rows;
+      if (used32[slot]) check(cudaEventSynchronize(r.e32[slot]), "event sync");
+      float* hs = hslot + (size_t)slot * slot_floats;
+      const double* src0 = X[j] + b0 * ldj;
+      const auto t0 = std::chrono::steady_clock::now();
+#pragma omp parallel for schedule(static) num_threads(host_threads_)
+      for (int64_t i = 0; i < rows; ++i) {
+        const double* src = src0 + i * ldj;
+        float* dst = hs + i * ldx;
+        for (int d = 0; d < D; ++d) dst[d] = (float)(src[d] - mu[d]);
+        for (int64_t d = D; d < ldx; ++d) dst[d] = 0.f;
+      }
+      const double tc = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      check(cudaMemcpyAsync((float*)v.X + (row0 + b0) * ldx, hs, sizeof(float) * (size_t)rows * ldx, cudaMemcpyHostToDevice,
+                            r.s32),
+            "H2D fp32 rows");
+      check(cudaEventRecord(r.e32[slot], r.s32), "event record");
+      used32[slot] = true;
+      slot = (slot + 1) % kSlots;
+      back = b0;
+      // ---- raw lane: as many fp64 rows from the front as fit into the link time that conversion left idle ----
+      if (pinned_src && front < back) {
+        const double idle = tc - (double)rows * ldx * 4 / kLinkBytesPerSec;
+        const int64_t fit = idle > 0 ? (int64_t)(idle * kLinkBytesPerSec / (8.0 * D)) : 0;
+        const int64_t rrows = std::min(std::min(fit, 2 * crow), back - front);
+        if (rrows >= 256) {
+          if (!r.dstage[rslot]) dev_alloc(&r.dstage[rslot], sizeof(double) * (size_t)(2 * crow) * D);
+          if (usedraw[rslot]) check(cudaEventSynchronize(r.eraw[rslot]), "event sync");
+          check(cudaMemcpyAsync(r.dstage[rslot], X[j] + front * ldj, sizeof(double) * (size_t)rrows * D,
+                                cudaMemcpyHostToDevice, r.sraw),
+                "H2D raw rows");
+          check(dev::convert_rows<float>(r.sraw, (const double*)r.dstage[rslot], rrows, D, D, 0, d_mean,
+                                         (float*)v.X + (row0 + front) * ldx, ldx),
+                "convert_rows");
+          check(cudaEventRecord(r.eraw[rslot], r.sraw), "event record");
+          usedraw[rslot] = true;
+          rslot ^= 1;
+          front += rrows;
+        }
+      }
+    }
+    row0 += n;
+  }
+  check(cudaStreamSynchronize(r.s32), "upload sync");
+  check(cudaStreamSynchronize(r.sraw), "upload sync");
+}
+
 void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int D, const int64_t* ld, int layout) {
   if (J < 1 || D < 1 || X == nullptr || Nj == nullptr) throw_invalid("set_data: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
@@ -399,7 +500,8 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
       for (int64_t n = 0; n < Nj[j]; ++n) g[o++] = j;
     check(cudaMemcpy(main_.gid, g.data(), sizeof(int32_t) * N, cudaMemcpyHostToDevice), "H2D gid");
   }
-  if (prec_ == kF32) upload_rows<float>(main_, X, Nj, ld, J, layout, centre_);
+  if (prec_ == kF32 && layout == 0) upload_rows_f32(main_, X, Nj, ld, J, centre_);
+  else if (prec_ == kF32) upload_rows<float>(main_, X, Nj, ld, J, layout, centre_);
   else upload_rows<double>(main_, X, Nj, ld, J, layout, centre_);
   measure_absmax(main_);
   clusters_.clear();
@@ -591,7 +693,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
       const double span = std::max(xabs_max_ + cmax, 1e-30);
       const float scale = (float)std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(16384.0 / span)))));
       reserve(d_err_, 16);
-      ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, lq, d_koff, d_tot, list_maxcnt_, list_nnz_, K,
+      ke = dev::sstat_tc128(stream_, sms_, (const float*)v.X, lrow, lq, d_koff, d_tot, list_maxcnt_, list_nnz_, K,
                             (const float*)d_cen_.p, scale, d_xs, d_S, (unsigned*)d_err_.p);
     } else if (v.N > 0) {
       const int64_t nb = dev::nz_blocks(v.N);
@@ -630,7 +732,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
             const double span = std::max(xabs_max_ + cmax, 1e-30);
             const float scale = (float)std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(16384.0 / span)))));
             reserve(d_err_, 16);
-            ke = dev::sstat_tc128(stream_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, maxcnt, nnz, K,
+            ke = dev::sstat_tc128(stream_, sms_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, maxcnt, nnz, K,
                                   (const float*)d_cen_.p, scale, d_xs, d_S, (unsigned*)d_err_.p);
           } else {
             ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
@@ -1552,7 +1654,8 @@ void Engine::op_addobs(ClusterPost& c, const double* qk, const double* X, int64_
     const double* Xs[1] = {X};
     const int64_t Ns[1] = {N};
     const int64_t lds[1] = {ld};
-    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    if (prec_ == kF32 && layout == 0) upload_rows_f32(tmp, Xs, Ns, lds, 1, centre_);
+    else if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
     else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, centre_);
     ensure_q(tmp, 1);
     tmp.K = 1;
@@ -1608,7 +1711,8 @@ void Engine::op_eloglike(const ClusterPost& c, const double* X, int64_t N, int64
     const double* Xs[1] = {X};
     const int64_t Ns[1] = {N};
     const int64_t lds[1] = {ld};
-    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
+    if (prec_ == kF32 && layout == 0) upload_rows_f32(tmp, Xs, Ns, lds, 1, centre_);
+    else if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, centre_);
     else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, centre_);
     ensure_q(tmp, 1);
     tmp.K = 1;
@@ -1652,7 +1756,8 @@ void Engine::op_splitobs(const ClusterPost& c, const double* X, int64_t N, int64
     const double* Xs[1] = {X};
     const int64_t Ns[1] = {N};
     const int64_t lds[1] = {ld};
-    if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, ctr);
+    if (prec_ == kF32 && layout == 0) upload_rows_f32(tmp, Xs, Ns, lds, 1, ctr);
+    else if (prec_ == kF32) upload_rows<float>(tmp, Xs, Ns, lds, 1, layout, ctr);
     else upload_rows<double>(tmp, Xs, Ns, lds, 1, layout, ctr);
     std::vector<double> dir;
     c.split_direction(dir);

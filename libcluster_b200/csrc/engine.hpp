@@ -76,6 +76,8 @@ class Engine {
   void op_splitobs(const ClusterPost& c, const double* X, int64_t N, int64_t ld, int layout, uint8_t* out);
 
  private:
+  void upload_rows_f32(View& v, const double* const* X, const int64_t* Nj, const int64_t* ld, int J,
+                       const std::vector<double>& mean);
   template <typename T> void upload_rows(View& v, const double* const* X, const int64_t* Nj, const int64_t* ld, int J,
                                          int layout, const std::vector<double>& mean);
   void free_view(View& v);

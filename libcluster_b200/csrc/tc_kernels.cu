@@ -47,6 +47,10 @@ constexpr uint32_t kOffMean = 49152;              // offset of the mean vectors 
 constexpr int kStages = 4;
 constexpr uint32_t kOffBar = kStages * kBBlob;    // 200704
 constexpr uint32_t kSmemBytes = kOffBar + 256 + 1024;
+constexpr uint32_t kTransRow = 272;               // list mode: 64 fp32 of a row + 16 B of padding (conflict-free transposition)
+constexpr uint32_t kTransWarp = 32 * kTransRow;   // one builder warp's gather buffer
+constexpr uint32_t kOffTrans = 2 * kBBlob;        // list mode: behind its two operand stages
+static_assert(kOffTrans + 8 * kTransWarp <= kOffBar, "gather buffers overlap the barriers");
 constexpr int kThreadsTc = 512;               // 4 control + 4 epilogue + 8 operand-builder warps
 constexpr uint32_t kTmemCols = 512;               // D0 [0,128) D1 [128,256) A0 hi/lo [256,384) A1 hi/lo [384,512)
 
@@ -130,18 +134,6 @@ __device__ __forceinline__ void tc_mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, 
         ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc)
         : "memory");
   }
-}
-// The same with the shared-memory descriptor given as two 32-bit words (lo = start address field | LBO, hi = SBO,
-// version, swizzle): the issuing warp then advances a descriptor with one 32-bit uniform add.
-__device__ __forceinline__ void tc_mma_f16_ts_w(uint32_t d_tmem, uint32_t a_tmem, uint32_t blo, uint32_t bhi,
-                                                uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t.reg .b64 bd;\n\t"
-      "setp.ne.b32 p, %5, 0;\n\t"
-      "mov.b64 bd, {%2, %3};\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}"
-      ::"r"(d_tmem), "r"(a_tmem), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO = 1024 B, descriptor version 1, SWIZZLE_128B
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
@@ -268,6 +260,8 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = kList ? nitems : (N + kTM - 1) / kTM;
+  // list mode keeps two operand stages and gives the rest of shared memory to the builders' gather buffers
+  constexpr uint32_t NS = kList ? 2u : (uint32_t)kStages;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -310,7 +304,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
           k1 = k0 + 1;
         }
         for (int k = k0; k < k1; ++k, ++cnt) {
-          const uint32_t st = cnt % kStages, ph = (cnt / kStages) & 1;
+          const uint32_t st = cnt % NS, ph = (cnt / NS) & 1;
           mbar_wait(bar(BB_EMPTY0 + st), ph ^ 1, err);
           mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
           bulk_g2s(sB + st * kBBlob, blob + (size_t)k * kBBlob, kBBlob, bar(BB_FULL0 + st));
@@ -325,7 +319,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
       for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int nk = kList ? 1 : K;
         for (int k = 0; k < nk; ++k, ++cnt) {
-          const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
+          const uint32_t bs = cnt % NS, bph = (cnt / NS) & 1;
           const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
           mbar_wait(bar(BT_EMPTY0 + st), ph ^ 1, err);
           mbar_wait(bar(BB_FULL0 + bs), bph, err);
@@ -457,9 +451,28 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         if (row < item.y) nn = (int64_t)__ldg(lrow + (((long long)(unsigned)item.z) | ((long long)item.w << 32)) + row);
       }
     };
+    // Gathered rows (list mode): a thread reading its own row makes every load instruction touch 32 cache lines
+    // (the L1 data pipe ran at 74 % and bounded the kernel, profiles/ncu_r01_refine_v4_raw.csv).  Instead the warp
+    // copies two rows per instruction (16 lanes x 16 B each) into its private shared-memory buffer with cp.async, one
+    // item ahead, so the gather latency hides behind the operand build of the current item.
+    auto gather_rows = [&](int64_t nrow) {
+      const uint32_t tbs = sbase + kOffTrans + (uint32_t)(warp - 8) * kTransWarp;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int rr = 2 * j + (lane >> 4);
+        const int64_t nr = __shfl_sync(0xffffffffu, nrow, rr);
+        const bool ok = nr < N;
+        const float* src = X + (ok ? nr : 0) * kD + 64 * kb + 4 * (lane & 15);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tbs + (uint32_t)rr * kTransRow + 16u * (uint32_t)(lane & 15)),
+                     "l"(src), "r"(ok ? 16u : 0u)
+                     : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
     if constexpr (kList) {
       fetch(blockIdx.x, k_cur, n_cur);
       fetch((int64_t)blockIdx.x + gridDim.x, k_nx, n_nx);
+      gather_rows(n_cur);
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       int64_t n = tile * kTM + row;
@@ -470,7 +483,20 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         n = n_cur;
       }
       float4 x[16];
-      if (n < N) {
+      if constexpr (kList) {
+        // The rows of this item were requested while the previous item was being built (gather_rows below): wait
+        // for them, then transpose through the warp's private buffer: lane r takes row r.
+        unsigned char* tb = sgen + kOffTrans + (uint32_t)(warp - 8) * kTransWarp;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float4*>(tb + lane * kTransRow + 16 * j);
+        __syncwarp();
+        k_cur = k_nx;
+        n_cur = n_nx;
+        fetch(tile + 2 * (int64_t)gridDim.x, k_nx, n_nx);
+        gather_rows(n_cur);
+      } else if (n < N) {
         const float4* src = reinterpret_cast<const float4*>(X + n * kD + 64 * kb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = __ldg(src + j);
@@ -478,18 +504,8 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      if constexpr (kList) {
-        if (n_nx < N) {
-          const float* nxt = X + n_nx * kD + 64 * kb;
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(nxt + 32));
-        }
-        k_cur = k_nx;
-        n_cur = n_nx;
-        fetch(tile + 2 * (int64_t)gridDim.x, k_nx, n_nx);
-      }
       for (int k = k0; k < k1; ++k, ++cnt) {
-        const uint32_t bs = cnt % kStages, bph = (cnt / kStages) & 1;
+        const uint32_t bs = cnt % NS, bph = (cnt / NS) & 1;
         const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
         const float sc = ascale[k];
         const float2 s2 = make_float2(sc, sc);
@@ -539,44 +555,59 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 
 
 // ===========================================================================
-// sstat_tc128_kernel: centred scatter of one cluster over a chunk of its list of
-// non-zero responsibilities, D == 128:
+// sstat_tc128_kernel: centred scatter over the per-cluster lists of non-zero
+// responsibilities, D == 128:
 //     S_k += sum_r (x_r - c_k) q_r (x_r - c_k)^T ,   xs_k += sum_r q_r (x_r - c_k)
 // as a 128 x 128 x (rows) GEMM on tcgen05: A = s (X - c)^T [dims x rows] lives in
 // TMEM, B = q s (X - c) [dims x rows, rows contiguous] in swizzled shared memory,
 // both split into fp16 (hi, lo) with the three significant products accumulated in
-// one fp32 TMEM accumulator.  s is a power of two that cannot saturate fp16 for any
-// row of the data set (engine: 2^14 / max|x - c|).  A thread owns one dimension
-// (= TMEM lane = B row) and 64 of the 128 rows of a tile; rows are gathered from X
-// through the per-cluster (row, q) lists built by nz_fill.  The accumulator covers
-// at most kScatterChunk rows (<= 128 tensor-core additions per element) before it
-// is added, in fp64, to the global statistics.
+// fp32 TMEM accumulators.  s is a power of two that cannot saturate fp16 for any
+// row of the data set (engine: 2^14 / max|x - c|).  A builder thread owns one
+// dimension (= TMEM lane = B row) and 64 of the 128 rows of a tile; rows are
+// gathered from X through the (row, q) lists.
+//
+// A work item is a chunk of at most chunk_rows list entries of one cluster: the
+// accumulators cover that many rows (<= 32 tensor-core additions per element at
+// 512) before they are added, in fp64, to the global statistics -- the tensor core
+// truncates when it adds into fp32, and the bias of a long chain would show in the
+// covariances.  One persistent CTA per SM walks the items; four flush warps move a
+// finished accumulator to the fp64 statistics while the builders and the MMA warp
+// already work on the next item (the first version launched one CTA per item and
+// spent more than half of its time in prologue, first-gather latency and the
+// flush, profiles/ncu_r01_sstat_v4_raw.csv).
+//   warp 0      list loader: (row, q) of the next 128 entries into shared memory
+//   warp 1      MMA issue
+//   warp 2      TMEM allocation
+//   warps 4-7   flush: tcgen05.ld of both accumulators, fp64 atomics
+//   warps 8-15  builders
 // ===========================================================================
-constexpr int kScatterThreads = 384;  // 4 control warps + 8 builder warps
+constexpr int kScatterThreads = 512;
 constexpr uint32_t kSB_Stage = 65536; // per stage: K block 0 (hi 16K, lo 16K), K block 1 (hi, lo)
 constexpr uint32_t kSOffList = 2 * kSB_Stage;
-constexpr uint32_t kSOffBar = kSOffList + 2 * 128 * 8;
+constexpr uint32_t kSOffPre = kSOffList + 2 * 128 * 8;        // item prefix per cluster: (kTcCoarseMaxK + 1) ints
+constexpr uint32_t kSOffBar = kSOffPre + 4 * (kTcCoarseMaxK + 8);
 constexpr uint32_t kSSmemBytes = kSOffBar + 256 + 1024;
-enum { SL_FULL0 = 0, SL_EMPTY0 = 2, SAB_FULL00 = 4 /* [stage][h] */, SAB_EMPTY00 = 8, SACC_FULL = 12, SB_COUNT = 13 };
+enum {
+  SL_FULL0 = 0, SL_EMPTY0 = 2, SAB_FULL00 = 4 /* [stage][h] */, SAB_EMPTY00 = 8, SACC_FULL = 12, SACC_EMPTY = 13,
+  SB_COUNT = 14
+};
+
+struct ScatterItem {
+  int k, ntile;
+  long long l0, l1, base;
+};
 
 __global__ void __launch_bounds__(kScatterThreads, 1)
 sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow, const float* __restrict__ lq,
-                   const long long* __restrict__ koff, const long long* __restrict__ kcnt,
+                   const long long* __restrict__ koff, const long long* __restrict__ kcnt, int K,
                    const float* __restrict__ cen, float scale, int chunk_rows, double* __restrict__ xs,
                    double* __restrict__ S, unsigned* __restrict__ err) {
-  const int k = blockIdx.y;
-  const long long cnt = kcnt[k];
-  const long long l0 = (long long)blockIdx.x * chunk_rows;
-  if (l0 >= cnt) return;
-  const long long l1 = (l0 + chunk_rows < cnt) ? l0 + chunk_rows : cnt;
-  const long long base = koff[k];
-  const int ntile = (int)((l1 - l0 + 127) / 128);
-
   extern __shared__ unsigned char smem_dyn[];
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
   const uint32_t sBar = sbase + kSOffBar;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kSOffBar + 8 * SB_COUNT);
+  int* pre = reinterpret_cast<int*>(sgen + kSOffPre);  // pre[k] = items of the clusters before k
   auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -590,7 +621,14 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
       mbar_init(bar(SAB_EMPTY00 + i), 1);
     }
     mbar_init(bar(SACC_FULL), 1);
+    mbar_init(bar(SACC_EMPTY), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int acc = 0;
+    for (int k = 0; k < K; ++k) {
+      pre[k] = acc;
+      acc += (int)((kcnt[k] + chunk_rows - 1) / chunk_rows);
+    }
+    pre[K] = acc;
   }
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
@@ -603,133 +641,106 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ---- list loader: (row, q) of the next 128 list entries into shared memory ----
-    for (int t = 0; t < ntile; ++t) {
-      const int st = t & 1;
-      mbar_wait(bar(SL_EMPTY0 + st), ((t >> 1) & 1) ^ 1, err);
-      int2* dst = reinterpret_cast<int2*>(sgen + kSOffList + st * 1024);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const long long l = l0 + (long long)t * 128 + e * 32 + lane;
-        int2 v = make_int2(-1, 0);
-        if (l < l1) {
-          v.x = lrow[base + l];
-          v.y = __float_as_int(lq[base + l]);
-        }
-        dst[e * 32 + lane] = v;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(SL_FULL0 + st));
+  const int nitems = pre[K];
+  // item -> (cluster, list range): the last cluster whose prefix is <= it
+  auto item_of = [&](int it) {
+    int lo = 0, hi = K - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (pre[mid] <= it) lo = mid;
+      else hi = mid - 1;
     }
-  } else if (warp == 1) {
-    // ---- MMA issuer ----
-    for (int t = 0; t < ntile; ++t) {
-      const int st = t & 1;
-      const uint32_t ph = (t >> 1) & 1;
-      const uint32_t a_hi0 = tmem_base + 128 + st * 128, a_lo0 = a_hi0 + 64;
+    ScatterItem r;
+    r.k = lo;
+    const long long cnt = kcnt[lo];
+    r.l0 = (long long)(it - pre[lo]) * chunk_rows;
+    r.l1 = r.l0 + chunk_rows < cnt ? r.l0 + chunk_rows : cnt;
+    r.base = koff[lo];
+    r.ntile = (int)((r.l1 - r.l0 + 127) / 128);
+    return r;
+  };
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ---- list loader: (row, q) of the next 128 list entries into shared memory ----
+      uint32_t tc = 0;
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+        const ScatterItem w = item_of(it);
+        for (int t = 0; t < w.ntile; ++t, ++tc) {
+          const uint32_t st = tc & 1;
+          mbar_wait(bar(SL_EMPTY0 + st), ((tc >> 1) & 1) ^ 1, err);
+          int2* dst = reinterpret_cast<int2*>(sgen + kSOffList + st * 1024);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        mbar_wait(bar(SAB_FULL00 + 2 * st + h), ph, err);
-        tc_fence_after();
-        const uint32_t b_hi = sbase + st * kSB_Stage + h * 32768, b_lo = b_hi + 16384;
-        const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
-        const uint32_t id = umma_idesc(128);
-        if (elect_one()) {
-#pragma unroll
-          // The hi*hi products and the 2^-11 smaller cross terms go to separate accumulators: the tensor core
-          // truncates when it adds into the fp32 accumulator, and the bias of a chain of n additions (~ n/2 ulp of the
-          // running sum) must stay ~1e-7 relative for the statistics, so the big chain is kept as short as possible.
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint64_t off = (uint64_t)((32 * c4) >> 4);
-            const uint32_t acol = 32 * h + 8 * c4;
-            const uint32_t first = (t == 0 && h == 0 && c4 == 0) ? 0u : 1u;
-            tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, first);
-            tc_mma_f16_ts(tmem_base + 384, a_hi0 + acol, dbl0 + off, id, first);
-            tc_mma_f16_ts(tmem_base + 384, a_lo0 + acol, dbh0 + off, id, 1u);
+          for (int e = 0; e < 4; ++e) {
+            const long long l = w.l0 + (long long)t * 128 + e * 32 + lane;
+            int2 v = make_int2(-1, 0);
+            if (l < w.l1) {
+              v.x = lrow[w.base + l];
+              v.y = __float_as_int(lq[w.base + l]);
+            }
+            dst[e * 32 + lane] = v;
           }
-          tc_commit(bar(SAB_EMPTY00 + 2 * st + h));
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(SL_FULL0 + st));
         }
+      }
+    } else if (warp == 1) {
+      // ---- MMA issuer ----
+      uint32_t tc = 0, ic = 0;
+      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++ic) {
+        const ScatterItem w = item_of(it);
+        // the flush warps must have read the previous item's accumulators
+        mbar_wait(bar(SACC_EMPTY), (ic & 1) ^ 1, err);
+        tc_fence_after();
+        for (int t = 0; t < w.ntile; ++t, ++tc) {
+          const uint32_t st = tc & 1;
+          const uint32_t ph = (tc >> 1) & 1;
+          const uint32_t a_hi0 = tmem_base + 256 + st * 128, a_lo0 = a_hi0 + 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            mbar_wait(bar(SAB_FULL00 + 2 * st + h), ph, err);
+            tc_fence_after();
+            const uint32_t b_hi = sbase + st * kSB_Stage + h * 32768, b_lo = b_hi + 16384;
+            const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
+            const uint32_t id = umma_idesc(128);
+            if (elect_one()) {
+              // The hi*hi products and the 2^-11 smaller cross terms go to separate accumulators: the tensor core
+              // truncates when it adds into the fp32 accumulator, and the bias of a chain of n additions (~ n/2 ulp
+              // of the running sum) must stay ~1e-7 relative for the statistics, so the big chain is kept short.
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                const uint64_t off = (uint64_t)((32 * c4) >> 4);
+                const uint32_t acol = 32 * h + 8 * c4;
+                const uint32_t first = (t == 0 && h == 0 && c4 == 0) ? 0u : 1u;
+                tc_mma_f16_ts(tmem_base, a_hi0 + acol, dbh0 + off, id, first);
+                tc_mma_f16_ts(tmem_base + 128, a_hi0 + acol, dbl0 + off, id, first);
+                tc_mma_f16_ts(tmem_base + 128, a_lo0 + acol, dbh0 + off, id, 1u);
+              }
+              tc_commit(bar(SAB_EMPTY00 + 2 * st + h));
+            }
+            __syncwarp();
+          }
+        }
+        if (elect_one()) tc_commit(bar(SACC_FULL));
         __syncwarp();
       }
     }
-    if (elect_one()) tc_commit(bar(SACC_FULL));
-    __syncwarp();
-  } else if (warp >= 4) {
-    // ---- builders: thread = dimension i (TMEM lane, B row), half h of the tile's rows ----
-    const int quad = warp & 3, h = (warp - 4) >> 2;
+  } else if (warp < 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+    // ---- flush: accumulators -> fp64 global statistics (S is symmetric: lane i writes column i) ----
+    const int quad = warp & 3;
     const int i = 32 * quad + lane;
-    const float ncs = -cen[(size_t)k * kD + i] * scale;
-    double xs64 = 0.0;
-    for (int t = 0; t < ntile; ++t) {
-      const int st = t & 1;
-      const uint32_t ph = (t >> 1) & 1;
-      mbar_wait(bar(SL_FULL0 + st), ph, err);
-      const int2* lst = reinterpret_cast<const int2*>(sgen + kSOffList + st * 1024) + 64 * h;
-      float a[64];
-#pragma unroll
-      for (int r = 0; r < 64; ++r) {
-        const int row = lst[r].x;
-        a[r] = row >= 0 ? __ldg(X + (size_t)row * kD + i) : 0.f;
-      }
-      float xs32 = 0.f;
-      mbar_wait(bar(SAB_EMPTY00 + 2 * st + h), ph ^ 1, err);
+    const double inv_s = 1.0 / (double)scale, inv_s2 = inv_s * inv_s;
+    uint32_t ic = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++ic) {
+      const ScatterItem w = item_of(it);
+      double* Sk = S + (size_t)w.k * kD * kD;
+      mbar_wait(bar(SACC_FULL), ic & 1, err);
       tc_fence_after();
-      const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 128 + st * 128 + 32 * h;
-      const uint32_t bRow = sbase + st * kSB_Stage + h * 32768 + (uint32_t)i * 128u;
-#pragma unroll
-      for (int g = 0; g < 2; ++g) {  // 32 rows per group: 16 packed columns of A, 4 chunks of B
-        uint32_t ah[16], al[16];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t bh[4], bl[4];
-#pragma unroll
-          for (int p = 0; p < 4; ++p) {
-            const int r = 32 * g + 8 * c + 2 * p;
-            const int2 e0 = lst[r], e1 = lst[r + 1];
-            const float q0 = __int_as_float(e0.y), q1 = __int_as_float(e1.y);
-            const float a0 = e0.x >= 0 ? fmaf(a[r], scale, ncs) : 0.f;
-            const float a1 = e1.x >= 0 ? fmaf(a[r + 1], scale, ncs) : 0.f;
-            const uint32_t hh = pack_f16x2_sat(a0, a1);
-            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
-            ah[4 * c + p] = hh;
-            al[4 * c + p] = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
-            const float v0 = q0 * a0, v1 = q1 * a1;
-            xs32 += v0 + v1;
-            const uint32_t vh = pack_f16x2_sat(v0, v1);
-            const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vh));
-            bh[p] = vh;
-            bl[p] = pack_f16x2_sat(v0 - vf.x, v1 - vf.y);
-          }
-          const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 16384u), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
-        }
-        tmem_st16(tA + 16 * g, ah);
-        tmem_st16(tA + 64 + 16 * g, al);
-      }
-      xs64 += (double)xs32;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(bar(SAB_FULL00 + 2 * st + h));
-        mbar_arrive(bar(SL_EMPTY0 + st));
-      }
-    }
-    const double inv_s = 1.0 / (double)scale;
-    if (xs64 != 0.0) atomicAdd(&xs[(size_t)k * kD + i], xs64 * inv_s);
-    if (h == 0) {
-      // ---- epilogue: accumulator -> fp64 global statistics (S is symmetric: lane i writes column i) ----
-      mbar_wait(bar(SACC_FULL), 0, err);
-      tc_fence_after();
-      const double inv_s2 = inv_s * inv_s;
-      double* Sk = S + (size_t)k * kD * kD;
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32];
+        uint32_t r[32], r2[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -740,7 +751,6 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
               "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 32 * cc)
             : "memory");
-        uint32_t r2[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -749,15 +759,91 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
               "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
               "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
               "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
-            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 384 + 32 * cc)
+            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 128 + 32 * cc)
             : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (cc == 3) {
+          // everything has been read: the next item may overwrite the accumulators while the last adds go out
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar(SACC_EMPTY));
+        }
 #pragma unroll
         for (int jj = 0; jj < 32; ++jj) {
           const double v = ((double)__uint_as_float(r[jj]) + (double)__uint_as_float(r2[jj])) * inv_s2;
           if (v != 0.0) atomicAdd(&Sk[(size_t)(32 * cc + jj) * kD + i], v);
         }
       }
+    }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    // ---- builders: thread = dimension i (TMEM lane, B row), half h of the tile's rows ----
+    const int quad = warp & 3, h = (warp - 8) >> 2;
+    const int i = 32 * quad + lane;
+    const double inv_s = 1.0 / (double)scale;
+    uint32_t tc = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+      const ScatterItem w = item_of(it);
+      const float ncs = -cen[(size_t)w.k * kD + i] * scale;
+      double xs64 = 0.0;
+      for (int t = 0; t < w.ntile; ++t, ++tc) {
+        const uint32_t st = tc & 1;
+        const uint32_t ph = (tc >> 1) & 1;
+        mbar_wait(bar(SL_FULL0 + st), ph, err);
+        const int2* lst = reinterpret_cast<const int2*>(sgen + kSOffList + st * 1024) + 64 * h;
+        float a[64];
+#pragma unroll
+        for (int r = 0; r < 64; ++r) {
+          const int row = lst[r].x;
+          a[r] = row >= 0 ? __ldg(X + (size_t)row * kD + i) : 0.f;
+        }
+        float xs32 = 0.f;
+        mbar_wait(bar(SAB_EMPTY00 + 2 * st + h), ph ^ 1, err);
+        tc_fence_after();
+        const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 256 + st * 128 + 32 * h;
+        const uint32_t bRow = sbase + st * kSB_Stage + h * 32768 + (uint32_t)i * 128u;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {  // 32 rows per group: 16 packed columns of A, 4 chunks of B
+          uint32_t ah[16], al[16];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t bh[4], bl[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              const int r = 32 * g + 8 * c + 2 * p;
+              const int2 e0 = lst[r], e1 = lst[r + 1];
+              const float q0 = __int_as_float(e0.y), q1 = __int_as_float(e1.y);
+              const float a0 = e0.x >= 0 ? fmaf(a[r], scale, ncs) : 0.f;
+              const float a1 = e1.x >= 0 ? fmaf(a[r + 1], scale, ncs) : 0.f;
+              const uint32_t hh = pack_f16x2_sat(a0, a1);
+              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+              ah[4 * c + p] = hh;
+              al[4 * c + p] = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
+              const float v0 = q0 * a0, v1 = q1 * a1;
+              xs32 += v0 + v1;
+              const uint32_t vh = pack_f16x2_sat(v0, v1);
+              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vh));
+              bh[p] = vh;
+              bl[p] = pack_f16x2_sat(v0 - vf.x, v1 - vf.y);
+            }
+            const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 16384u), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
+          }
+          tmem_st16(tA + 16 * g, ah);
+          tmem_st16(tA + 64 + 16 * g, al);
+        }
+        xs64 += (double)xs32;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar(SAB_FULL00 + 2 * st + h));
+          mbar_arrive(bar(SL_EMPTY0 + st));
+        }
+      }
+      if (xs64 != 0.0) atomicAdd(&xs[(size_t)w.k * kD + i], xs64 * inv_s);
     }
   }
 
@@ -790,8 +876,8 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
 // chains: 16 warps =
 //   warp 0      producer: cp.async.bulk of B_k (24 KB, 3-stage ring) and of the
 //               aug blocks (16 KB per 4 clusters, 2-stage ring)
-//   warp 1      MMA issue: per (cluster, tile) 1 aug + 8 triangular chunk MMAs
-//   warp 2      TMEM allocation
+//   warps 1-3   MMA issue, one warp per tile slot: per (cluster, tile) item 1 aug +
+//               8 triangular chunk MMAs (coarse_mma_issuer); warp 2 also allocates TMEM
 //   warps 4-7   stagers: X -> fp16 staging in shared memory during the previous
 //               group, staging -> TMEM A at the group boundary; they also turn the
 //               parked UB rows of the finished group into the candidate marking
@@ -1271,79 +1357,94 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
 // ---------------------------------------------------------------------------
 // Level 3: row soft-max over the candidate logits in q (cmask: W words per row):
 // q = exp(logit - log Z) for candidates, 0 elsewhere; Fz += sum_n log Z_n.
-// LPR lanes share a row (NV float4 each), a warp keeps 4 * 32 / LPR rows in flight.
+// The first version gave every 16-byte group of a row to a lane and ran the whole
+// soft-max arithmetic on all of them; with one or two candidates per row it was
+// issue-bound (84 % issue slots, 143 warp instructions per row,
+// profiles/ncu_r01_finalize_v5_raw.csv).  Now a warp takes 32 rows:
+//   phase A  lane = row: walk the set bits of the row's mask, max and sum of
+//            exponentials over its candidates only; exp(logit - max) is parked
+//            in place
+//   phase B  GP lanes per row: rewrite the row as parked value / sum under the
+//            mask, zeros elsewhere (only groups that hold a candidate are read)
+// so the pass costs the row write plus a sector or two of reads per row.
 // ---------------------------------------------------------------------------
-template <int LPR, int NV>
-__global__ void __launch_bounds__(256, NV == 1 ? 4 : 2)
+template <int LGP>  // log2 of the lanes that share a row in phase B: 4 << LGP >= K
+__global__ void __launch_bounds__(256)
 estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, const uint32_t* __restrict__ cmask, int W,
                       double* __restrict__ Fz) {
-  constexpr int RPW = 32 / LPR, U = 4;
-  const int lane = threadIdx.x & 31, sub = lane % LPR, rsel = lane / LPR;
+  constexpr int GP = 1 << LGP, WMAX = (4 * GP + 31) / 32;
+  const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   double fz = 0;
-  for (int64_t r0 = warp0 * (U * RPW); r0 < N; r0 += nwarps * (U * RPW)) {
-    float4 v[U][NV];
-    uint32_t m[U][NV];
+  for (int64_t r0 = warp0 * 32; r0 < N; r0 += nwarps * 32) {
+    // ---- phase A ----
+    const int64_t n = r0 + lane;
+    uint32_t mw[WMAX];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t n = r0 + u * RPW + rsel;
+    for (int w = 0; w < WMAX; ++w) mw[w] = (n < N && w < W) ? __ldg(cmask + n * W + w) : 0u;
+    float* qrow = q + (n < N ? n : 0) * ldq;
+    float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = 4 * sub + 4 * LPR * j;
-        m[u][j] = (n < N && k < K) ? (__ldg(cmask + n * W + (k >> 5)) >> (k & 31)) & 0xFu : 0u;
+    for (int w = 0; w < WMAX; ++w) {
+      uint32_t word = mw[w];
+      while (word) {
+        const int k = 32 * w + __ffs(word) - 1;
+        word &= word - 1;
+        mx = fmaxf(mx, qrow[k]);
       }
     }
-    // only the 16-byte groups that hold a candidate are read: q is otherwise write-only here (the non-candidate
-    // entries still hold level-1 bounds nobody needs), which halves the HBM traffic of the pass
+    float se = 0.f;
+    if (mx > -INFINITY) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t n = r0 + u * RPW + rsel;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = 4 * sub + 4 * LPR * j;
-        v[u][j] = m[u][j] ? *reinterpret_cast<const float4*>(q + n * ldq + k) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int64_t n = r0 + u * RPW + rsel;
-      float e[4 * NV];
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = 4 * sub + 4 * LPR * j;
-        const float x[4] = {v[u][j].x, v[u][j].y, v[u][j].z, v[u][j].w};
-#pragma unroll
-        for (int i = 0; i < 4; ++i) e[4 * j + i] = (((m[u][j] >> i) & 1u) && k + i < K) ? x[i] : -INFINITY;
-      }
-      float mx = e[0];
-#pragma unroll
-      for (int i = 1; i < 4 * NV; ++i) mx = fmaxf(mx, e[i]);
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const bool any = mx > -INFINITY;
-      float se = 0.f;
-#pragma unroll
-      for (int i = 0; i < 4 * NV; ++i) se += any ? expf(e[i] - mx) : 0.f;  // exp(-inf) = 0
-#pragma unroll
-      for (int o = LPR / 2; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-      const float lz = any ? logf(se) + mx : 0.f;
-      if (n >= N) continue;
-#pragma unroll
-      for (int j = 0; j < NV; ++j) {
-        const int k = 4 * sub + 4 * LPR * j;
-        float o4[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) o4[i] = any ? expf(e[4 * j + i] - lz) : 0.f;
-        if (k + 4 <= K) {
-          *reinterpret_cast<float4*>(q + n * ldq + k) = make_float4(o4[0], o4[1], o4[2], o4[3]);
-        } else {
-          for (int i = 0; i < 4; ++i)
-            if (k + i < K) q[n * ldq + k + i] = o4[i];
+      for (int w = 0; w < WMAX; ++w) {
+        uint32_t word = mw[w];
+        while (word) {
+          const int k = 32 * w + __ffs(word) - 1;
+          word &= word - 1;
+          const float e = expf(qrow[k] - mx);
+          qrow[k] = e;
+          se += e;
         }
       }
-      if (sub == 0) fz += (double)lz;
+      fz += (double)(logf(se) + mx);
     }
+    const float inv = se > 0.f ? 1.0f / se : 0.f;
+    __syncwarp();  // the parked values are read by other lanes below
+    // ---- phase B ----
+#pragma unroll 4
+    for (int idx = lane; idx < 32 * GP; idx += 32) {
+      const int row = idx >> LGP, g = idx & (GP - 1);
+      const float invr = __shfl_sync(0xffffffffu, inv, row);
+      uint32_t word = 0;
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) {
+        const uint32_t t = __shfl_sync(0xffffffffu, mw[w], row);
+        if ((g >> 3) == w) word = t;
+      }
+      const uint32_t nib = (word >> ((4 * g) & 31)) & 0xFu;
+      const int64_t nr = r0 + row;
+      const int k = 4 * g;
+      if (nr < N && k < K) {
+        float* dst = q + nr * ldq + k;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nib) {
+          const float4 v = *reinterpret_cast<const float4*>(dst);
+          o.x = (nib & 1u) ? v.x * invr : 0.f;
+          o.y = (nib & 2u) ? v.y * invr : 0.f;
+          o.z = (nib & 4u) ? v.z * invr : 0.f;
+          o.w = (nib & 8u) ? v.w * invr : 0.f;
+        }
+        if (k + 4 <= K) {
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          dst[0] = o.x;
+          if (k + 1 < K) dst[1] = o.y;
+          if (k + 2 < K) dst[2] = o.z;
+        }
+      }
+    }
+    __syncwarp();
   }
   for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
   if (lane == 0 && fz != 0.0) atomicAdd(Fz, fz);
@@ -1497,10 +1598,10 @@ cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int6
   if (K > 256 || (ldq & 3)) return cudaErrorInvalidValue;
   const int W = (K + 31) / 32;
   const int grid = sms * 16;
-  if (K <= 32) estep_finalize_kernel<8, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else if (K <= 64) estep_finalize_kernel<16, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else if (K <= 128) estep_finalize_kernel<32, 1><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else estep_finalize_kernel<32, 2><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  if (K <= 32) estep_finalize_kernel<3><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else if (K <= 64) estep_finalize_kernel<4><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else if (K <= 128) estep_finalize_kernel<5><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  else estep_finalize_kernel<6><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
   return cudaGetLastError();
 }
 
@@ -1568,20 +1669,21 @@ double tc_pack_aug(const double* w /* [128] */, int k, uint8_t* augblob) {
   return worst;
 }
 
-cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
-                        const long long* kcnt, long long maxcnt, long long nnz, int K, const float* cen, float scale,
-                        double* xs, double* S, unsigned* err) {
+cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t* lrow, const float* lq,
+                        const long long* koff, const long long* kcnt, long long maxcnt, long long nnz, int K,
+                        const float* cen, float scale, double* xs, double* S, unsigned* err) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
   // rows folded into one fp32 TMEM accumulator before the fp64 add: fewer for small problems (more accurate, and the
   // extra atomics are free there), kTcScatterChunk for large ones
   const int chunk_rows = nnz <= (1LL << 20) ? 128 : kTcScatterChunk;
   cudaError_t e = cudaFuncSetAttribute(sstat_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes);
   if (e != cudaSuccess) return e;
-  const long long chunks = (maxcnt + chunk_rows - 1) / chunk_rows;
-  if (chunks > 2147483647LL || K > 65535) return cudaErrorInvalidValue;
-  dim3 grid((unsigned)chunks, K);
-  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, cen, scale, chunk_rows, xs, S,
-                                                                 err);
+  // persistent CTAs walk the (cluster, chunk) items; no more CTAs than items
+  const long long items_max = (nnz + chunk_rows - 1) / chunk_rows + K;
+  if (K > kTcCoarseMaxK || items_max > 2000000000LL) return cudaErrorInvalidValue;
+  const int grid = (int)(items_max < sms ? items_max : sms);
+  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, K, cen, scale, chunk_rows, xs,
+                                                                 S, err);
   return cudaGetLastError();
 }
 

@@ -54,9 +54,9 @@ double tc_pack_aug(const double* w, int k, uint8_t* augblob);
 // Centred scatter over the per-cluster non-zero lists (see tc_kernels.cu); cen [K][128] is relative to the data
 // centre, scale a power of two with scale * max|x - c| <= 2^14.
 constexpr int kTcScatterChunk = 512;  // list rows folded into the fp32 accumulators before the fp64 add (32 tensor-core additions)
-cudaError_t sstat_tc128(cudaStream_t st, const float* X, const int32_t* lrow, const float* lq, const long long* koff,
-                        const long long* kcnt, long long maxcnt, long long nnz, int K, const float* cen, float scale,
-                        double* xs, double* S, unsigned* err);
+cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t* lrow, const float* lq,
+                        const long long* koff, const long long* kcnt, long long maxcnt, long long nnz, int K,
+                        const float* cen, float scale, double* xs, double* S, unsigned* err);
 
 void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
 

@@ -46,3 +46,34 @@ def test_operator_argument_checks():
         c.addobs(np.ones(10), X)                       # distributions.cpp:303-304
     with pytest.raises(lc.InvalidArgument, match="not the same length"):
         c.addobs(np.ones(9), np.zeros((10, 3)))        # :305-306
+
+
+def test_upload_lanes_give_identical_resident_data():
+    """lcb_set_data on a page-locked matrix splits the rows between host-converted fp32 blocks and raw fp64 blocks
+    converted on the device (engine.cu: upload_rows_f32); a pageable matrix takes the first lane only.  Both must
+    leave the same X on the device, so one VB iteration gives the same F and qZ."""
+    import torch
+
+    for N, D, K in ((150_000, 128, 4), (400_000, 6, 3)):   # D = 6: rows padded to 8 columns on the device
+        X, z = make_blobs(N, D, K, seed=5, spread=4.0)
+        q0 = np.full((N, K), 0.01)
+        q0[np.arange(N), z] = 1.0 - 0.01 * (K - 1)
+        Xp = torch.empty(N, D, dtype=torch.float64, pin_memory=True)
+        Xp.copy_(torch.from_numpy(X))
+        out = []
+        for src in (X, Xp.numpy()):
+            eng = lc.Engine(0, lc.F32)
+            eng.set_data(src)
+            eng.model_init(lc.BGMM)
+            eng.set_qz(q0)
+            F, _ = eng.vbem(maxit=0)
+            out.append((F, eng.qZ(0)))
+            eng.set_data(src)            # a second upload of the same shape reuses the device buffers
+            eng.model_init(lc.BGMM)
+            eng.set_qz(q0)
+            F2, _ = eng.vbem(maxit=0)
+            assert F2 == pytest.approx(F, rel=1e-8)
+            eng.close()
+        # (the statistics are summed with fp64 atomics, and fp32 partial sums depend on the order of arrival: runs agree to ~1e-10, not bit for bit)
+        assert out[0][0] == pytest.approx(out[1][0], rel=1e-8)
+        assert np.abs(out[0][1] - out[1][1]).max() <= 1e-6
