@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "liblcb200.so")
+LIB_PATH = os.environ.get("LCB_LIB_PATH") or os.path.join(HERE, "_lib", "liblcb200.so")  # override: diagnostic builds
 
 OK, EINVAL, ERUNTIME, EDOMAIN, ECUDA, ENOMEM = range(6)
 VDP, BGMM, DGMM, GMC, SGMC, DGMC = range(6)

@@ -106,6 +106,10 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
     const int n = std::atoi(ht);
     if (n >= 1 && n <= 1024) host_threads_ = n;
   }
+  if (const char* cv = std::getenv("LCB_COARSE_VARIANT")) {
+    const int n = std::atoi(cv);  // 2, 3; 3 + bit mask = timing experiments of the three-accumulator kernel
+    if (n >= 2 && n <= 18) coarse_variant_ = n;
+  }
   if (const char* sg = std::getenv("LCB_TC_STAGE")) {
     if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
     else if (std::strcmp(sg, "refine") == 0) tc_stage_ = 2;
@@ -1009,6 +1013,11 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   double out[2] = {0, 0};
   check(cudaMemcpyAsync(out, d_fz, sizeof(double) * 2, cudaMemcpyDeviceToHost, stream_), "D2H Fz");
   sync();
+  if (estep_detail_[5] == 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ev_[4], ev_[5]) == cudaSuccess) estep_detail_[0] = ms;  // level 1 ran, then the dense kernel
+    else cudaGetLastError();
+  }
   if (estep_detail_[5] == 1) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ev_[4], ev_[5]);
@@ -1043,7 +1052,7 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
   for (int attempt = 0;; ++attempt) {
     check(cudaEventRecord(ev_[4], stream_), "event");
     check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
-                                  d_act, sg, aug_exp, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, d_err),
+                                  d_act, sg, aug_exp, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, coarse_variant_, d_err),
           "estep_coarse_tc128 launch");
     ++launches_;
     check(cudaEventRecord(ev_[5], stream_), "event");
