@@ -106,10 +106,6 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
     const int n = std::atoi(ht);
     if (n >= 1 && n <= 1024) host_threads_ = n;
   }
-  if (const char* cv = std::getenv("LCB_COARSE_VARIANT")) {
-    const int n = std::atoi(cv);  // 2, 3; 3 + bit mask = timing experiments of the three-accumulator kernel
-    if (n >= 2 && n <= 18) coarse_variant_ = n;
-  }
   if (const char* sg = std::getenv("LCB_TC_STAGE")) {
     if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
     else if (std::strcmp(sg, "refine") == 0) tc_stage_ = 2;
@@ -212,6 +208,7 @@ void Engine::comm_init_nccl(const char id[128], int rank, int world) {
   host_ar_ = nullptr;
   rank_ = rank;
   world_ = world;
+  share_host_threads();
 }
 
 void Engine::comm_init_host(HostAllreduceFn fn, void* ctx, int rank, int world) {
@@ -220,6 +217,15 @@ void Engine::comm_init_host(HostAllreduceFn fn, void* ctx, int rank, int world) 
   host_ar_ctx_ = ctx;
   rank_ = rank;
   world_ = world;
+  share_host_threads();
+}
+
+// One process per GPU on one box: every rank runs the same replicated host-side updates, so the ranks share the
+// cores instead of each starting hardware_concurrency() threads.
+void Engine::share_host_threads() {
+  if (std::getenv("LCB_HOST_THREADS") != nullptr || world_ <= 1) return;
+  const int hw = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+  host_threads_ = std::max(2, hw / std::min(world_, 8));
 }
 
 void Engine::allreduce(double* dev, int64_t count) {
@@ -1052,7 +1058,7 @@ bool Engine::ephase_two_level(View& v, int K, const uint8_t* d_blob, const float
   for (int attempt = 0;; ++attempt) {
     check(cudaEventRecord(ev_[4], stream_), "event");
     check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
-                                  d_act, sg, aug_exp, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, coarse_variant_, d_err),
+                                  d_act, sg, aug_exp, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, d_err),
           "estep_coarse_tc128 launch");
     ++launches_;
     check(cudaEventRecord(ev_[5], stream_), "event");

@@ -106,6 +106,7 @@ class Engine {
   void build_act(const std::vector<double>& Njk, int J, int K);
   void allreduce(double* dev, int64_t count);
   void allreduce_host(double* host, int64_t count);
+  void share_host_threads();
   void check(cudaError_t e, const char* what) const;
   void sync();
 
@@ -115,7 +116,6 @@ class Engine {
   // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
   bool use_two_level_ = true;
   int host_threads_ = 1;        // threads of the host-side posterior updates (engine.cu)
-  int coarse_variant_ = 3;      // level-1 kernel: 3 accumulators x 2 tile slots, or 2 x 3 (LCB_COARSE_VARIANT)
   int tc_stage_ = 0;            // 0 full, 1 stop after level 1, 2 stop after level 2
   int two_level_skip_ = 0;      // iterations left before the two-level path is tried again after it did not pay
   uint32_t coarse_sbase_hint_ = 1024;  // shared-memory base the level-1 kernel takes as a parameter (tc_kernels.cuh)

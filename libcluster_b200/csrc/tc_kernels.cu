@@ -952,31 +952,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-#ifdef LCB_COARSE_TRACE
-// Diagnostic build only (tools/coarse_trace.py): CTA 0 records (tag, item, SM clock) of the accumulator hand-off.
-// tags: 1 issuer saw the accumulator drained, 2 issuer done issuing, 3 epilogue woke on "accumulator full",
-//       4 epilogue loads complete, 5 epilogue released the accumulator
-constexpr int kTraceMax = 1 << 16;
-__device__ unsigned long long g_trace[kTraceMax];
-__device__ unsigned int g_trace_n;
-__device__ __forceinline__ void trace_put(uint32_t tag, uint32_t item, uint32_t who, uint32_t clk) {
-  if (blockIdx.x != 0 || item >= 4096u) return;
-  const unsigned int i = atomicAdd(&g_trace_n, 1u);
-  if (i < (unsigned)kTraceMax)
-    g_trace[i] = ((unsigned long long)tag << 60) | ((unsigned long long)who << 56) | ((unsigned long long)item << 32) | clk;
-}
-__device__ __forceinline__ uint32_t trace_clock() {
-  uint32_t c;
-  asm volatile("mov.u32 %0, %%clock;" : "=r"(c));
-  return c;
-}
-#define LCB_TRACE_ASM_T0 "mov.u32 t, %%clock;\n\tst.shared.u32 [%10], t;\n\t"
-#define LCB_TRACE_ASM_T1 "mov.u32 t, %%clock;\n\tst.shared.u32 [%10+4], t;\n\t"
-#else
-#define LCB_TRACE_ASM_T0
-#define LCB_TRACE_ASM_T1
-#endif
-
 // ---------------------------------------------------------------- MMA issuers of the level-1 kernel --
 // Three issuing warps, one per tile slot S of the group; item (k, S) is the ic-th item of this CTA,
 // ic = 3 (K g + k) + S, and uses accumulator ic & 1.  One issuer needs ~850 cycles of dependent uniform-datapath
@@ -1029,7 +1004,6 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
             "sub.u32 t, t, %1;\n\t"
             "setp.lt.s32 q, t, 0;\n\t"
             "@q bra CW_WAIT_%=;\n\t"
-            LCB_TRACE_ASM_T0
             "tcgen05.fence::after_thread_sync;\n\t"
             "mov.b64 bd, {%6, %7};\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3+64], bd, 0x8200010, !p;\n\t"
@@ -1057,22 +1031,10 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
             "tcgen05.mma.cta_group::1.kind::f16 [%2+112], [%3+56], bd, 0x8040010, p;\n\t"
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-            LCB_TRACE_ASM_T1
             "}"
             ::"r"(barb + 8u * C_COUNT + 16u + 4u * acc), "r"(4u * (ic >> 1)), "r"(128u * acc), "r"(a0), "r"(lo0), "r"(lo1),
               "r"(log_), "r"(kDescHi), "r"(barb + 8u * (CT_FULL0 + acc)), "r"(barb + 8u * (CB_EMPTY0 + bs))
-#ifdef LCB_COARSE_TRACE
-              , "r"(barb + 8u * C_COUNT + 32u + 8u * S)
-#endif
             : "memory");
-#ifdef LCB_COARSE_TRACE
-        {
-          uint32_t c0, c1;
-          asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(c0), "=r"(c1) : "r"(barb + 8u * C_COUNT + 32u + 8u * S));
-          trace_put(1, ic, S, c0);
-          trace_put(2, ic, S, c1);
-        }
-#endif
         if (aug_done) tc_commit(barb + 8u * (CG_EMPTY0 + as));
         if (last) tc_commit(barb + 8u * (CA_FREE0 + S));
       }
@@ -1351,23 +1313,14 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
           }
           const float e = fmaf(ek, xn[s], ea);
           mbar_wait(bfull, (icnt >> 1) & 1, err);
-#ifdef LCB_COARSE_TRACE
-          if (lane == 0 && quad == 0) trace_put(3, icnt, 8 + grp, trace_clock());
-#endif
           tc_fence_after();
           uint32_t r[128];
           tmem_ld64(tacc, r);
           tmem_ld64(tacc + 64u, r + 64);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#ifdef LCB_COARSE_TRACE
-          if (lane == 0 && quad == 0) trace_put(4, icnt, 8 + grp, trace_clock());
-#endif
           tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(drained) : "memory");
-#ifdef LCB_COARSE_TRACE
-          if (lane == 0 && quad == 0) trace_put(5, icnt, 8 + grp, trace_clock());
-#endif
           const float ss = sumsq128(r);
           if (qrow[s] != nullptr) {
             float d;
@@ -1391,552 +1344,6 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       __threadfence_block();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(CL_FULL0 + p));
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
-  }
-}
-
-// ===========================================================================
-// Level 1, three-accumulator variant (K % 4 == 0): estep_coarse3_tc128_kernel.
-//
-// Same arithmetic and outputs as estep_coarse_tc128_kernel.  That kernel's tensor pipe
-// is 68 % busy because an accumulator's cycle -- nine MMAs issued (~400 clocks), commit,
-// epilogue wake-up, tcgen05.ld, release, issuer notices (~600 clocks) -- is longer than
-// the MMAs of the one other accumulator that could fill the gap.  A third accumulator
-// closes it.  TMEM has room for three (384 columns) only with two tile slots of A
-// (2 x 64 columns), so
-//   * a group is 2 tiles (256 rows); a cluster's operand is used by two MMA chains
-//     (L2 -> shared-memory traffic 12 KB per item instead of 8 KB);
-//   * the constant A operand of the aug chunk (2^P in three slots) moves to shared
-//     memory: one 128-row swizzled K-major tile written at kernel start and read by
-//     an SS-mode MMA, instead of 8 TMEM columns per tile slot.
-// Item ic = 2 (K g + k) + s of a CTA (g-th group, cluster k, tile slot s) uses accumulator
-// ic % 3; issuer warp w owns accumulator w.  Epilogue group e owns tile slot e (the parity
-// of ic).  "Accumulator full" uses two mbarriers per accumulator, by the parity of its use
-// count u = ic / 3: (3u + a) & 1 is constant for fixed a and u & 1, so each barrier is always
-// waited on by the same epilogue group, phase after phase.  "Accumulator drained" is a
-// counter in shared memory (four arrivals per use).
-// ===========================================================================
-constexpr int kET = 2;
-constexpr int kERows = kET * kTM;                                    // 256 rows per group
-constexpr uint32_t kEOffAug = kCStages * kCBStage;                   // 73728
-constexpr uint32_t kEOffStageA = kEOffAug + 2 * kTcAugBlockBytes;    // 106496
-constexpr uint32_t kEOffAugA = kEOffStageA + kET * kCStageA;         // 172032: A tile of the aug chunk, [128 rows][128 B]
-constexpr uint32_t kEOffPar = kEOffAugA + 16384;                     // 188416: per-cluster floats [4][256]
-constexpr uint32_t kEOffLb = kEOffPar + 4 * 256 * 4;                 // 192512: [2 parities][256] lower-bound maxima
-constexpr uint32_t kEOffBar = kEOffLb + 2 * kERows * 4;              // 194560
-constexpr uint32_t kESmemBytes = kEOffBar + 512 + 1024;
-static_assert(kEOffAugA % 1024 == 0, "swizzled tiles are 1024-byte aligned");
-enum {
-  EB_FULL0 = 0, EB_EMPTY0 = 3, EG_FULL0 = 6, EG_EMPTY0 = 8, EA_READY0 = 10, EA_FREE0 = 12, ET_FULL0 = 14 /* [acc][u & 1] */,
-  EL_FULL0 = 20, EL_FREE0 = 22, E_COUNT = 24
-};
-constexpr uint32_t kEOffDrain = 8 * E_COUNT + 16;                    // three u32 counters behind the TMEM slot
-
-template <uint32_t W>
-__device__ __forceinline__ void coarse3_mma_issuer(uint32_t sb, int K, int64_t ngroups, int mode, unsigned* err) {
-  const uint32_t barb = sb + kEOffBar;
-  const uint32_t blo_base = umma_desc_lo(sb), glo_base = umma_desc_lo(sb + kEOffAug), alo = umma_desc_lo(sb + kEOffAugA);
-  const uint32_t Ku = (uint32_t)K, nblk = Ku >> 2;  // aug blocks per group (K % 4 == 0)
-  const int64_t my_groups = (int64_t)blockIdx.x < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const uint64_t total = (uint64_t)my_groups * 2u * Ku;  // items of this CTA
-  uint32_t g = 0, k = W >> 1, s = W & 1u;               // item W: cluster W / 2, slot W % 2 of group 0
-  uint32_t u = 0, last_blk = 0xffffffffu;
-  for (uint64_t ic = W; ic < total; ic += 3, ++u) {
-    const uint32_t kk = g * Ku + k;                     // clusters streamed so far: position in the operand ring
-    const uint32_t bs = kk % (uint32_t)kCStages, bph = (kk / (uint32_t)kCStages) & 1u;
-    const uint32_t blk = g * nblk + (k >> 2), as = blk & 1u;
-    if (blk != last_blk) {
-      mbar_wait(barb + 8u * (EG_FULL0 + as), (blk >> 1) & 1u, err);
-      last_blk = blk;
-    }
-    mbar_wait(barb + 8u * (EB_FULL0 + bs), bph, err);
-    const uint32_t pos = 2u * k + s;                    // position inside the group; this issuer's items on a slot are 6 apart
-    if (pos < 6u) mbar_wait(barb + 8u * (EA_READY0 + s), g & 1u, err);
-    const uint32_t lo0 = blo_base + bs * (kCBStage >> 4), lo1 = lo0 + (16384u >> 4);
-    const uint32_t log_ = glo_base + as * (kTcAugBlockBytes >> 4) + 2u * (k & 3u);
-    // where this issuer goes next (item ic + 3)
-    uint32_t k2 = k + 1u + s, g2 = g;
-    const uint32_t s2 = s ^ 1u;
-    if (k2 >= Ku) {
-      k2 -= Ku;
-      ++g2;
-    }
-    const bool aug_done = ic + 3 >= total || g2 * nblk + (k2 >> 2) != blk;  // its last item on this aug block
-    const bool slot_done = pos + 6u >= 2u * Ku;                             // ... and on this tile slot's A operand
-    if (mode & 8) {
-      // timing experiment: the aug chunk and chunks 0-3 only (half of the tensor work; results are wrong)
-      if (elect_one()) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q, r;\n\t"
-            ".reg .b64 bd, ad;\n\t"
-            ".reg .b32 t, c;\n\t"
-            "setp.ne.b32 p, 1, 0;\n\t"
-            "mov.u32 c, 0;\n\t"
-            "C3H_WAIT_%=:\n\t"
-            "add.u32 c, c, 1;\n\t"
-            "setp.gt.u32 r, c, 67108864;\n\t"
-            "@r trap;\n\t"
-            "ld.acquire.cta.shared.u32 t, [%0];\n\t"
-            "sub.u32 t, t, %1;\n\t"
-            "setp.lt.s32 q, t, 0;\n\t"
-            "@q bra C3H_WAIT_%=;\n\t"
-            "tcgen05.fence::after_thread_sync;\n\t"
-            "mov.b64 ad, {%10, %7};\n\t"
-            "mov.b64 bd, {%6, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2], ad, bd, 0x8200010, !p;\n\t"
-            "mov.b64 bd, {%4, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], bd, 0x8200010, p;\n\t"
-            "add.u32 t, %4, 0x82;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+16], [%3+8], bd, 0x81c0010, p;\n\t"
-            "add.u32 t, %4, 0x104;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+32], [%3+16], bd, 0x8180010, p;\n\t"
-            "add.u32 t, %4, 0x186;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+48], [%3+24], bd, 0x8140010, p;\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-            "}"
-            ::"r"(barb + kEOffDrain + 4u * W), "r"(4u * u), "r"(128u * W), "r"(384u + 64u * s), "r"(lo0), "r"(lo1), "r"(log_),
-              "r"(kDescHi), "r"(barb + 8u * (ET_FULL0 + 2u * W + (u & 1u))), "r"(barb + 8u * (EB_EMPTY0 + bs)), "r"(alo)
-            : "memory");
-        if (aug_done) tc_commit(barb + 8u * (EG_EMPTY0 + as));
-        if (slot_done) tc_commit(barb + 8u * (EA_FREE0 + s));
-      }
-    } else if (mode & 1) {
-      // experiment: output columns [64,128) and [0,64) as two independent accumulate chains, issued alternately
-      // (14 MMAs instead of 9, same tensor work): separates a per-instruction cost from a same-accumulator dependency
-      if (elect_one()) {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p, q, r;\n\t"
-            ".reg .b64 bd, ad;\n\t"
-            ".reg .b32 t, c;\n\t"
-            "setp.ne.b32 p, 1, 0;\n\t"
-            "mov.u32 c, 0;\n\t"
-            "C3S_WAIT_%=:\n\t"
-            "add.u32 c, c, 1;\n\t"
-            "setp.gt.u32 r, c, 67108864;\n\t"
-            "@r trap;\n\t"
-            "ld.acquire.cta.shared.u32 t, [%0];\n\t"
-            "sub.u32 t, t, %1;\n\t"
-            "setp.lt.s32 q, t, 0;\n\t"
-            "@q bra C3S_WAIT_%=;\n\t"
-            "tcgen05.fence::after_thread_sync;\n\t"
-            "mov.b64 ad, {%10, %7};\n\t"
-            "add.u32 t, %6, 512;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], ad, bd, 0x8100010, !p;\n\t"
-            "mov.b64 bd, {%6, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2], ad, bd, 0x8100010, !p;\n\t"
-            "add.u32 t, %4, 512;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3], bd, 0x8100010, p;\n\t"
-            "mov.b64 bd, {%4, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], bd, 0x8100010, p;\n\t"
-            "add.u32 t, %4, 514;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+8], bd, 0x8100010, p;\n\t"
-            "add.u32 t, %4, 0x82;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+16], [%3+8], bd, 0x80c0010, p;\n\t"
-            "add.u32 t, %4, 516;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+16], bd, 0x8100010, p;\n\t"
-            "add.u32 t, %4, 0x104;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+32], [%3+16], bd, 0x8080010, p;\n\t"
-            "add.u32 t, %4, 518;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+24], bd, 0x8100010, p;\n\t"
-            "add.u32 t, %4, 0x186;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+48], [%3+24], bd, 0x8040010, p;\n\t"
-            "mov.b64 bd, {%5, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+32], bd, 0x8100010, p;\n\t"
-            "add.u32 t, %5, 0x82;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+80], [%3+40], bd, 0x80c0010, p;\n\t"
-            "add.u32 t, %5, 0x104;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+96], [%3+48], bd, 0x8080010, p;\n\t"
-            "add.u32 t, %5, 0x186;\n\t"
-            "mov.b64 bd, {t, %7};\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%2+112], [%3+56], bd, 0x8040010, p;\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-            "}"
-            ::"r"(barb + kEOffDrain + 4u * W), "r"(4u * u), "r"(128u * W), "r"(384u + 64u * s), "r"(lo0), "r"(lo1), "r"(log_),
-              "r"(kDescHi), "r"(barb + 8u * (ET_FULL0 + 2u * W + (u & 1u))), "r"(barb + 8u * (EB_EMPTY0 + bs)), "r"(alo)
-            : "memory");
-        if (aug_done) tc_commit(barb + 8u * (EG_EMPTY0 + as));
-        if (slot_done) tc_commit(barb + 8u * (EA_FREE0 + s));
-      }
-    } else if (elect_one()) {
-      // wait for the accumulator (4 u arrivals of the epilogue), then the aug chunk from shared memory (SS mode;
-      // accumulator = -s_g tau_k R_k m_k) and the eight triangular chunks with A in TMEM, then the commits
-      asm volatile(
-          "{\n\t"
-          ".reg .pred p, q, r;\n\t"
-          ".reg .b64 bd, ad;\n\t"
-          ".reg .b32 t, c;\n\t"
-          "setp.ne.b32 p, 1, 0;\n\t"
-          "mov.u32 c, 0;\n\t"
-          "C3_WAIT_%=:\n\t"
-          "add.u32 c, c, 1;\n\t"
-          "setp.gt.u32 r, c, 67108864;\n\t"
-          "@r trap;\n\t"
-          "ld.acquire.cta.shared.u32 t, [%0];\n\t"
-          "sub.u32 t, t, %1;\n\t"
-          "setp.lt.s32 q, t, 0;\n\t"
-          "@q bra C3_WAIT_%=;\n\t"
-          "tcgen05.fence::after_thread_sync;\n\t"
-          "mov.b64 ad, {%10, %7};\n\t"
-          "mov.b64 bd, {%6, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2], ad, bd, 0x8200010, !p;\n\t"
-          "mov.b64 bd, {%4, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], bd, 0x8200010, p;\n\t"
-          "add.u32 t, %4, 0x82;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+16], [%3+8], bd, 0x81c0010, p;\n\t"
-          "add.u32 t, %4, 0x104;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+32], [%3+16], bd, 0x8180010, p;\n\t"
-          "add.u32 t, %4, 0x186;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+48], [%3+24], bd, 0x8140010, p;\n\t"
-          "mov.b64 bd, {%5, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+64], [%3+32], bd, 0x8100010, p;\n\t"
-          "add.u32 t, %5, 0x82;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+80], [%3+40], bd, 0x80c0010, p;\n\t"
-          "add.u32 t, %5, 0x104;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+96], [%3+48], bd, 0x8080010, p;\n\t"
-          "add.u32 t, %5, 0x186;\n\t"
-          "mov.b64 bd, {t, %7};\n\t"
-          "tcgen05.mma.cta_group::1.kind::f16 [%2+112], [%3+56], bd, 0x8040010, p;\n\t"
-          "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
-          "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
-          "}"
-          ::"r"(barb + kEOffDrain + 4u * W), "r"(4u * u), "r"(128u * W), "r"(384u + 64u * s), "r"(lo0), "r"(lo1), "r"(log_),
-            "r"(kDescHi), "r"(barb + 8u * (ET_FULL0 + 2u * W + (u & 1u))), "r"(barb + 8u * (EB_EMPTY0 + bs)), "r"(alo)
-          : "memory");
-      if (aug_done) tc_commit(barb + 8u * (EG_EMPTY0 + as));
-      if (slot_done) tc_commit(barb + 8u * (EA_FREE0 + s));
-    }
-    __syncwarp();
-    k = k2;
-    s = s2;
-    g = g2;
-  }
-}
-
-__global__ void __launch_bounds__(kThreadsTc, 1)
-estep_coarse3_tc128_kernel(const float* __restrict__ X, const float* __restrict__ xnorm, int64_t N,
-                           const int32_t* __restrict__ gid, int K, const uint8_t* __restrict__ blob,
-                           const uint8_t* __restrict__ augblob, const float* __restrict__ cpar /* [4][K] */,
-                           const float* __restrict__ lw, const uint8_t* __restrict__ act, float sg, uint32_t aug01,
-                           uint32_t aug2, float margin, float* __restrict__ q, int64_t ldq,
-                           uint32_t* __restrict__ cmask, uint32_t sbase_hint, int mma_mode, unsigned* __restrict__ err) {
-  extern __shared__ unsigned char smem_dyn[];
-  uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
-  asm volatile("" : "+r"(sbase));
-  unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
-  asm volatile("" : "+l"(sgen));
-  const uint32_t sBar = sbase + kEOffBar;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(sgen + kEOffBar + 8 * E_COUNT);
-  auto bar = [&](int i) { return sBar + 8u * (uint32_t)i; };
-  float* spar = reinterpret_cast<float*>(sgen + kEOffPar);  // [0] cinv2, [1] Ek, [2] Ea, [3] chat; stride 256
-  float* slb = reinterpret_cast<float*>(sgen + kEOffLb);
-
-  uint32_t tid = threadIdx.x;
-  asm volatile("" : "+r"(tid));
-  // the issuers address shared memory through sbase_hint, a kernel parameter (see estep_coarse_tc128_kernel)
-  if (sbase != sbase_hint) {
-    if (tid == 0 && blockIdx.x == 0) err[1] = 0x80000000u | sbase;
-    return;
-  }
-  const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
-  const int64_t ngroups = (N + kERows - 1) / kERows;
-
-  if (tid == 0) {
-    for (int i = 0; i < kCStages; ++i) {
-      mbar_init(bar(EB_FULL0 + i), 1);
-      mbar_init(bar(EB_EMPTY0 + i), 2);  // the two issuers that hold the cluster's two items
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(bar(EG_FULL0 + i), 1);
-      mbar_init(bar(EG_EMPTY0 + i), 3);  // every issuer has items on an aug block (8 items)
-      mbar_init(bar(EA_READY0 + i), 4);  // 4 stager warps (lane quadrants)
-      mbar_init(bar(EA_FREE0 + i), 3);   // every issuer has items on a tile slot
-      mbar_init(bar(EL_FULL0 + i), 8);   // 8 epilogue warps
-      mbar_init(bar(EL_FREE0 + i), 4);   // 4 stager warps
-    }
-    for (int i = 0; i < 6; ++i) mbar_init(bar(ET_FULL0 + i), 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    for (int i = 0; i < 3; ++i) reinterpret_cast<volatile uint32_t*>(sgen + kEOffBar + kEOffDrain)[i] = 0u;
-  }
-  for (int i = (int)tid; i < 4 * 256; i += kThreadsTc) {
-    const int a = i >> 8, k = i & 255;
-    float val = k < K ? cpar[(size_t)a * K + k] : 0.f;
-    if (a == 3 && gid == nullptr && k < K) val += lw[k];  // single group: fold E[log pi_k] into the constant
-    spar[i] = val;
-  }
-  // A operand of the aug chunk: every row holds 2^P in its first three fp16 slots, zeros behind; K-major rows of
-  // 128 bytes, 16-byte chunks XOR-swizzled with row % 8 (the layout of the B blobs)
-  for (int i = (int)tid; i < 128 * 8; i += kThreadsTc) {
-    const int r = i >> 3, j = i & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (j == 0) {
-      v.x = aug01;
-      v.y = aug2;
-    }
-    *reinterpret_cast<uint4*>(sgen + kEOffAugA + r * 128 + ((j ^ (r & 7)) << 4)) = v;
-  }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
-                     smem_u32((const void*)tmem_slot)),
-                 "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  uint32_t tmem_base = *tmem_slot;
-  asm volatile("" : "+r"(tmem_base));
-  const bool tmem_ok = tmem_base == 0;  // all 512 columns are ours, so the allocation starts at column 0, lane 0
-  if (!tmem_ok && tid == 0) atomicExch(err, 0xdead7e00u);
-
-  if (!tmem_ok) {
-    // nothing: fall through to the dealloc
-  } else if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-    if (warp == 0 && lane == 0) {
-      // ---------------------------------------------------------- producer --
-      uint32_t bcnt = 0, acnt = 0;
-      for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x) {
-        for (int k = 0; k < K; ++k, ++bcnt) {
-          if ((k & 3) == 0) {
-            const uint32_t as = acnt & 1, aph = (acnt >> 1) & 1;
-            mbar_wait_patient(bar(EG_EMPTY0 + as), aph ^ 1, err);
-            mbar_expect_tx(bar(EG_FULL0 + as), kTcAugBlockBytes);
-            bulk_g2s(sbase + kEOffAug + as * kTcAugBlockBytes, augblob + (size_t)(k >> 2) * kTcAugBlockBytes,
-                     kTcAugBlockBytes, bar(EG_FULL0 + as));
-            ++acnt;
-          }
-          const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
-          mbar_wait_patient(bar(EB_EMPTY0 + bs), bph ^ 1, err);
-          mbar_expect_tx(bar(EB_FULL0 + bs), kCBStage);
-          const uint8_t* src = blob + (size_t)k * kBBlob;
-          bulk_g2s(sbase + bs * kCBStage, src, 16384u, bar(EB_FULL0 + bs));                  // hi, dims 0..63
-          bulk_g2s(sbase + bs * kCBStage + 16384u, src + 32768u, 8192u, bar(EB_FULL0 + bs));  // hi, dims 64..127
-        }
-      }
-    }
-    if (warp == 1) coarse3_mma_issuer<0>(sbase_hint, K, ngroups, mma_mode, err);
-    if (warp == 2) coarse3_mma_issuer<1>(sbase_hint, K, ngroups, mma_mode, err);
-    if (warp == 3) coarse3_mma_issuer<2>(sbase_hint, K, ngroups, mma_mode, err);
-  } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
-    // --------------------------------------------------------------- stagers --
-    const int sw = warp - 4;  // == lane quadrant of the TMEM rows this warp may touch
-    // X rows of group gi -> fp16(s_g x) in the staging buffers; a warp converts two rows per step
-    auto stage_group = [&](int64_t gi) {
-      for (int t = 0; t < kET; ++t) {
-        const int64_t n0 = gi * kERows + (int64_t)t * kTM;
-        unsigned char* dstT = sgen + kEOffStageA + (uint32_t)t * kCStageA;
-#pragma unroll 1
-        for (int it0 = 0; it0 < 16; it0 += 4) {
-          float4 v[4][2];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
-            const int64_t n = n0 + r;
-            if (n < N) {
-              const float4* src = reinterpret_cast<const float4*>(X + n * kD + 8 * (lane & 15));
-              v[u][0] = __ldg(src);
-              v[u][1] = __ldg(src + 1);
-            } else {
-              v[u][0] = v[u][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
-            uint4 w;
-            w.x = pack_f16x2_sat(v[u][0].x * sg, v[u][0].y * sg);
-            w.y = pack_f16x2_sat(v[u][0].z * sg, v[u][0].w * sg);
-            w.z = pack_f16x2_sat(v[u][1].x * sg, v[u][1].y * sg);
-            w.w = pack_f16x2_sat(v[u][1].z * sg, v[u][1].w * sg);
-            *reinterpret_cast<uint4*>(dstT + r * 256 + (((lane & 15) ^ (r & 15)) << 4)) = w;
-          }
-        }
-      }
-    };
-    // parked UB row of the finished group -> candidate bit mask (bit k of row n: UB_nk can reach e^-margin of the
-    // row's best lower bound)
-    auto mark_group = [&](int64_t gi, uint32_t parity) {
-      const float* lb0 = slb + parity * kERows;
-      const int W = (K + 31) >> 5;
-#pragma unroll 1
-      for (int t = 0; t < kET; ++t) {
-        const int r = t * kTM + sw * 32 + lane;
-        const int64_t n = gi * kERows + r;
-        if (n >= N) continue;
-        const float thr = lb0[r] - margin;
-        const float4* q4 = reinterpret_cast<const float4*>(q + n * ldq);
-        uint32_t* mrow = cmask + n * W;
-        uint32_t word = 0;
-        int wi = 0;
-        for (int k = 0; k < K; k += 4) {  // K % 4 == 0
-          const float4 v = __ldcg(q4 + (k >> 2));
-          const uint32_t b = (v.x >= thr ? 1u : 0u) | (v.y >= thr ? 2u : 0u) | (v.z >= thr ? 4u : 0u) | (v.w >= thr ? 8u : 0u);
-          word |= b << (k & 31);
-          if ((k & 31) == 28) {
-            mrow[wi++] = word;
-            word = 0;
-          }
-        }
-        if (K & 31) mrow[wi] = word;
-      }
-    };
-    uint32_t gcnt = 0;
-    int64_t gi = blockIdx.x, gprev = -1;
-    if (gi < ngroups) stage_group(gi);
-    named_bar_sync(1, 128);
-    for (; gi < ngroups; gi += gridDim.x, ++gcnt) {
-      // (a) staging -> TMEM A of every tile slot as soon as the previous group's MMAs released it
-      const int row = sw * 32 + lane;
-#pragma unroll 1
-      for (int s = 0; s < kET; ++s) {
-        mbar_wait_patient(bar(EA_FREE0 + s), (gcnt & 1) ^ 1, err);
-        tc_fence_after();
-        const unsigned char* srcT = sgen + kEOffStageA + (uint32_t)s * kCStageA + row * 256;
-        const uint32_t tA = tmem_base + ((uint32_t)(32 * sw) << 16) + 384u + 64u * (uint32_t)s;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) {
-          uint32_t rr[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 w = *reinterpret_cast<const uint4*>(srcT + (((4 * h + c) ^ (row & 15)) << 4));
-            rr[4 * c] = w.x;
-            rr[4 * c + 1] = w.y;
-            rr[4 * c + 2] = w.z;
-            rr[4 * c + 3] = w.w;
-          }
-          tmem_st16(tA + 16 * h, rr);
-        }
-        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(EA_READY0 + s));
-      }
-      named_bar_sync(1, 128);  // every stager is done reading the staging buffers
-      // (b) candidate marking of the group that just finished
-      if (gprev >= 0) {
-        const uint32_t p = (gcnt - 1) & 1;
-        mbar_wait_patient(bar(EL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
-        mark_group(gprev, p);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar(EL_FREE0 + p));
-      }
-      // (c) stage the next group while this one runs
-      if (gi + gridDim.x < ngroups) stage_group(gi + gridDim.x);
-      named_bar_sync(1, 128);
-      gprev = gi;
-    }
-    if (gprev >= 0) {
-      const uint32_t p = (gcnt - 1) & 1;
-      mbar_wait_patient(bar(EL_FULL0 + p), ((gcnt - 1) >> 1) & 1, err);
-      mark_group(gprev, p);
-    }
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
-    // -------------------------------------------------------------- epilogue --
-    // group e = tile slot e: its items are ic = 2 (K g + k) + e
-    const uint32_t e = (uint32_t)(warp - 8) >> 2;
-    const int quad = warp & 3;
-    const uint32_t tlane = tmem_base + ((uint32_t)(32 * quad) << 16);
-    const bool grouped = gid != nullptr;
-    const bool special = grouped || act != nullptr;  // per-row weights or an active mask: the rare, slower tail
-    const uint32_t spar_s = sbase + kEOffPar;
-    uint32_t gcnt = 0;
-    uint32_t a = e, u = 0;  // accumulator and use count of the next item: ic = e -> a = e, u = 0
-    for (int64_t gi = blockIdx.x; gi < ngroups; gi += gridDim.x, ++gcnt) {
-      const int64_t n = gi * kERows + (int64_t)e * kTM + 32 * quad + lane;
-      const bool valid = n < N;
-      float* qrow = valid ? q + n * ldq : nullptr;
-      const float xn = valid ? __ldg(xnorm + n) : 0.f;
-      const int gg = (grouped && valid) ? gid[n] : 0;
-      const float* lwg = lw + (size_t)gg * K;
-      const uint8_t* actg = act != nullptr ? act + (size_t)gg * K : nullptr;
-      float lbmax = -INFINITY;
-#pragma unroll 1
-      for (int k = 0; k < K; ++k) {
-        float cinv2, ek, ea, ch;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(cinv2) : "r"(spar_s + 4u * (uint32_t)k));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ek) : "r"(spar_s + 4u * (uint32_t)k + 1024u));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ea) : "r"(spar_s + 4u * (uint32_t)k + 2048u));
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ch) : "r"(spar_s + 4u * (uint32_t)k + 3072u));
-        // everything that does not depend on the accumulator first: its latency hides behind the wait
-        float c = ch;
-        bool off = false;
-        if (special) {
-          if (grouped) c += __ldg(lwg + k);
-          off = actg != nullptr && !__ldg(actg + k);
-        }
-        const float eb = fmaf(ek, xn, ea);
-        mbar_wait(bar(ET_FULL0 + 2 * (int)a + (int)(u & 1u)), (u >> 1) & 1u, err);
-        tc_fence_after();
-        uint32_t r[128];
-        if (!(mma_mode & 4)) {
-          tmem_ld64(tlane + 128u * a, r);
-          tmem_ld64(tlane + 128u * a + 64u, r + 64);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        } else {
-#pragma unroll
-          for (int i = 0; i < 128; ++i) asm volatile("" : "=r"(r[i]));  // timing experiment: whatever the registers hold
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(sBar + kEOffDrain + 4u * a) : "memory");
-        // next item of this group: ic + 2
-        a += 2u;
-        if (a >= 3u) {
-          a -= 3u;
-          ++u;
-        }
-        const float ss = (mma_mode & 2) ? __uint_as_float(r[0] ^ r[127]) : sumsq128(r);
-        if (qrow != nullptr && !((mma_mode & 2) && ss != 12345.f)) {
-          float d;
-          asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(ss * cinv2));
-          const float dlo = fmaxf(d - eb, 0.f), dhi = d + eb;
-          float ub = fmaf(-0.5f * dlo, dlo, c), lb = fmaf(-0.5f * dhi, dhi, c);
-          ub += 2e-6f * fabsf(ub) + 1e-3f;   // fp32 rounding of the bound itself (approximate square root)
-          lb -= 2e-6f * fabsf(lb) + 1e-3f;
-          if (off) ub = lb = -INFINITY;
-          qrow[k] = ub;
-          lbmax = fmaxf(lbmax, lb);
-        }
-      }
-      // hand the per-row maxima of the lower bounds to the stagers
-      const uint32_t p = gcnt & 1;
-      mbar_wait(bar(EL_FREE0 + p), ((gcnt >> 1) & 1) ^ 1, err);
-      slb[p * kERows + e * kTM + 32 * quad + lane] = lbmax;
-      __threadfence_block();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar(EL_FULL0 + p));
     }
   }
 
@@ -2172,41 +1579,18 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
                                float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
-                               int variant, unsigned* err) {
+                               unsigned* err) {
   if (N <= 0) return cudaSuccess;
   if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
-  const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
-  if (variant >= 3 && (K & 3) == 0) {
-    cudaError_t e3 = cudaFuncSetAttribute(estep_coarse3_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kESmemBytes);
-    if (e3 != cudaSuccess) return e3;
-    const int64_t ng3 = (N + kERows - 1) / kERows;
-    const int grid3 = (int)(ng3 < sms ? ng3 : sms);
-    estep_coarse3_tc128_kernel<<<grid3, kThreadsTc, kESmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
-                                                                       h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, variant >= 4 ? variant - 3 : 0, err);
-    return cudaGetLastError();
-  }
   cudaError_t e = cudaFuncSetAttribute(estep_coarse_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (N + kCRows - 1) / kCRows;
   const int grid = (int)(ngroups < sms ? ngroups : sms);
+  const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
   estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
                                                                    h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, err);
   return cudaGetLastError();
 }
-
-#ifdef LCB_COARSE_TRACE
-extern "C" int lcb_debug_read_trace(unsigned long long* out, int max_entries) {
-  unsigned int n = 0;
-  cudaDeviceSynchronize();
-  cudaMemcpyFromSymbol(&n, g_trace_n, sizeof(n));
-  int m = (int)(n < (unsigned)kTraceMax ? n : (unsigned)kTraceMax);
-  if (m > max_entries) m = max_entries;
-  cudaMemcpyFromSymbol(out, g_trace, sizeof(unsigned long long) * (size_t)m);
-  const unsigned int zero = 0;
-  cudaMemcpyToSymbol(g_trace_n, &zero, sizeof(zero));
-  return m;
-}
-#endif
 
 cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
                            double* Fz) {

@@ -27,9 +27,7 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
                                float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
-                               int variant, unsigned* err);
-// variant: 3 = three accumulators, two tile slots (estep_coarse3_tc128_kernel; needs K % 4 == 0, else falls back),
-//          2 = two accumulators, three tile slots (estep_coarse_tc128_kernel)
+                               unsigned* err);
 // err[1] of a launch whose sbase_hint did not match: 0x80000000 | the 1024-aligned shared-memory base to pass instead
 constexpr uint32_t kTcSbaseDefault = 1024;
 // candidate masks -> per-cluster row lists: mask_count, nz_scan (kernels.cuh), mask_fill

@@ -18,7 +18,7 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for (model, D, K, N, diag) in [(lc.BGMM, 128, 6, 30011, False), (lc.VDP, 16, 4, 9001, False), (lc.DGMM, 24, 5, 12345, True)]:
+    for (model, D, K, N, diag) in [(lc.BGMM, 128, 6, 30011, False), (lc.BGMM, 128, 16, 60011, False), (lc.VDP, 16, 4, 9001, False), (lc.DGMM, 24, 5, 12345, True)]:
         X, z = make_blobs(N, D, K, seed=N, spread=4.0, diag=diag)
         q0 = soft_labels(z, K, seed=3)
         ref = None
