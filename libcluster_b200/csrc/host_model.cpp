@@ -131,36 +131,72 @@ double WeightPost::fenergy() const {
 }
 
 // ------------------------------------------------------------ dense helpers --
-bool cholesky_lower(std::vector<double>& A, int D) {
-  for (int j = 0; j < D; ++j) {
-    double* rj = &A[(size_t)j * D];
-    double d = rj[j];
-    for (int p = 0; p < j; ++p) d -= rj[p] * rj[p];
-    if (!(d > 0.0)) return false;
-    d = std::sqrt(d);
-    rj[j] = d;
-    for (int i = j + 1; i < D; ++i) {
-      double* ri = &A[(size_t)i * D];
-      double t = ri[j];
-      for (int p = 0; p < j; ++p) t -= ri[p] * rj[p];
-      ri[j] = t / d;
-    }
-    for (int c = j + 1; c < D; ++c) rj[c] = 0.0;
-  }
+// The two O(D^3) routines of the host M step.  Their inner loops run along rows; each exists in a baseline build and
+// in an AVX2+FMA build chosen at run time (the library itself is compiled for generic x86-64).
+#define LCB_CHOLESKY_BODY                                            \
+  for (int j = 0; j < D; ++j) {                                      \
+    double* rj = A + (size_t)j * D;                                  \
+    double d = rj[j];                                                \
+    for (int p = 0; p < j; ++p) d -= rj[p] * rj[p];                  \
+    if (!(d > 0.0)) return false;                                    \
+    d = std::sqrt(d);                                                \
+    rj[j] = d;                                                       \
+    const double invd = 1.0 / d;                                     \
+    for (int i = j + 1; i < D; ++i) {                                \
+      double* ri = A + (size_t)i * D;                                \
+      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;                         \
+      int p = 0;                                                     \
+      for (; p + 4 <= j; p += 4) {                                   \
+        t0 += ri[p] * rj[p];                                         \
+        t1 += ri[p + 1] * rj[p + 1];                                 \
+        t2 += ri[p + 2] * rj[p + 2];                                 \
+        t3 += ri[p + 3] * rj[p + 3];                                 \
+      }                                                              \
+      for (; p < j; ++p) t0 += ri[p] * rj[p];                        \
+      ri[j] = (ri[j] - ((t0 + t1) + (t2 + t3))) * invd;              \
+    }                                                                \
+    for (int c = j + 1; c < D; ++c) rj[c] = 0.0;                     \
+  }                                                                  \
   return true;
+
+#define LCB_INVERT_BODY                                              \
+  for (int i = 0; i < D; ++i) {                                      \
+    double* ri = Li + (size_t)i * D;                                 \
+    const double* li = L + (size_t)i * D;                            \
+    for (int p = 0; p < i; ++p) {                                    \
+      const double f = li[p];                                        \
+      const double* rp = Li + (size_t)p * D;                         \
+      for (int c = 0; c <= p; ++c) ri[c] -= f * rp[c];               \
+    }                                                                \
+    const double inv = 1.0 / li[i];                                  \
+    for (int c = 0; c < i; ++c) ri[c] *= inv;                        \
+    ri[i] = inv;                                                     \
+  }
+
+static bool cholesky_generic(double* A, int D) { LCB_CHOLESKY_BODY }
+static void invert_generic(const double* L, int D, double* Li) { LCB_INVERT_BODY }
+#if defined(__x86_64__) && defined(__GNUC__)
+__attribute__((target("avx2,fma"))) static bool cholesky_avx2(double* A, int D) { LCB_CHOLESKY_BODY }
+__attribute__((target("avx2,fma"))) static void invert_avx2(const double* L, int D, double* Li) { LCB_INVERT_BODY }
+static bool have_avx2() {
+  static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma");
+  return ok;
+}
+#else
+static bool have_avx2() { return false; }
+static bool cholesky_avx2(double* A, int D) { return cholesky_generic(A, D); }
+static void invert_avx2(const double* L, int D, double* Li) { invert_generic(L, D, Li); }
+#endif
+
+bool cholesky_lower(std::vector<double>& A, int D) {
+  return have_avx2() ? cholesky_avx2(A.data(), D) : cholesky_generic(A.data(), D);
 }
 
 void invert_lower(const std::vector<double>& L, int D, std::vector<double>& Li) {
+  // row i of L^-1 = (e_i - sum_{p<i} L[i][p] * row p of L^-1) / L[i][i]
   Li.assign((size_t)D * D, 0.0);
-  for (int c = 0; c < D; ++c) {
-    Li[(size_t)c * D + c] = 1.0 / L[(size_t)c * D + c];
-    for (int i = c + 1; i < D; ++i) {
-      double t = 0;
-      const double* li = &L[(size_t)i * D];
-      for (int p = c; p < i; ++p) t -= li[p] * Li[(size_t)p * D + c];
-      Li[(size_t)i * D + c] = t / li[i];
-    }
-  }
+  if (have_avx2()) invert_avx2(L.data(), D, Li.data());
+  else invert_generic(L.data(), D, Li.data());
 }
 
 // --------------------------------------------------------------- clusters --

@@ -34,6 +34,12 @@
 #include "kernels.cuh"
 #include "tc_kernels.cuh"
 
+#include <cstring>
+
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#endif
+
 namespace lcb {
 namespace dev {
 
@@ -262,6 +268,12 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   const int64_t ntiles = kList ? nitems : (N + kTM - 1) / kTM;
   // list mode keeps two operand stages and gives the rest of shared memory to the builders' gather buffers
   constexpr uint32_t NS = kList ? 2u : (uint32_t)kStages;
+  // dense mode: tiles strided over the CTAs.  List mode: a contiguous range of items per CTA -- the items are sorted by
+  // cluster, so consecutive items mostly share their operand blob, which is then loaded once per run of equal
+  // clusters instead of once per item (50 KB from L2 each: it bounded the pass).
+  const int64_t tbeg = kList ? (nitems * (int64_t)blockIdx.x) / gridDim.x : (int64_t)blockIdx.x;
+  const int64_t tend = kList ? (nitems * ((int64_t)blockIdx.x + 1)) / gridDim.x : ntiles;
+  const int64_t tstep = kList ? 1 : (int64_t)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
@@ -293,15 +305,18 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   // Register budget per role (64K registers / SM): the control warps and the epilogue
   // hand registers to the operand builders, which keep 64 fp32 of X per thread.
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
     // ------------------------------------------------------------ producer --
     if (warp == 0 && lane == 0) {
       uint32_t cnt = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      int kprev = -1;
+      for (int64_t tile = tbeg; tile < tend; tile += tstep) {
         int k0 = 0, k1 = K;
         if constexpr (kList) {
           k0 = __ldg(items + tile).x;
           k1 = k0 + 1;
+          if (k0 == kprev) continue;  // the blob of this cluster is already on its way or resident
+          kprev = k0;
         }
         for (int k = k0; k < k1; ++k, ++cnt) {
           const uint32_t st = cnt % NS, ph = (cnt / NS) & 1;
@@ -315,14 +330,24 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     // The whole warp runs the loop so that addresses and descriptors live in uniform
     // registers; only the tcgen05 instructions themselves are issued by one elected lane.
     if (warp == 1) {
-      uint32_t cnt = 0;  // clusters processed so far (all rings advance once per cluster)
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      uint32_t cnt = 0;   // (tile, cluster) items processed so far: A and accumulator stages
+      uint32_t bidx = 0;  // operand blobs used so far: B stages (dense mode: one per item)
+      int kprev = -1;
+      for (int64_t tile = tbeg; tile < tend; tile += tstep) {
         const int nk = kList ? 1 : K;
+        bool newk = true, lastk = true;
+        if constexpr (kList) {
+          const int kc = __ldg(items + tile).x;
+          newk = kc != kprev;
+          kprev = kc;
+          lastk = tile + 1 >= tend || __ldg(items + tile + 1).x != kc;
+        }
         for (int k = 0; k < nk; ++k, ++cnt) {
-          const uint32_t bs = cnt % NS, bph = (cnt / NS) & 1;
+          if (newk) ++bidx;
+          const uint32_t bs = (bidx - 1) % NS, bph = ((bidx - 1) / NS) & 1;
           const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
           mbar_wait(bar(BT_EMPTY0 + st), ph ^ 1, err);
-          mbar_wait(bar(BB_FULL0 + bs), bph, err);
+          if (newk) mbar_wait(bar(BB_FULL0 + bs), bph, err);
           const uint32_t sBk = sB + bs * kBBlob;
           const uint32_t a_hi0 = tmem_base + 256 + st * 128, a_lo0 = a_hi0 + 64;
           const uint32_t d0 = tmem_base + st * 128;
@@ -349,7 +374,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
             __syncwarp();
           }
           if (elect_one()) {
-            tc_commit(bar(BB_EMPTY0 + bs));
+            if (lastk) tc_commit(bar(BB_EMPTY0 + bs));
             tc_commit(bar(BT_FULL0 + st));
           }
           __syncwarp();
@@ -368,15 +393,15 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     auto fetch = [&](int64_t it) {
       nk = 0;
       nn = -1;
-      if (it < ntiles) {
+      if (it < tend) {
         const int4 item = __ldg(items + it);
         nk = item.x;
         if (ew * 32 + lane < item.y)
           nn = (int64_t)__ldg(lrow + (((long long)(unsigned)item.z) | ((long long)item.w << 32)) + ew * 32 + lane);
       }
     };
-    if constexpr (kList) fetch(blockIdx.x);
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    if constexpr (kList) fetch(tbeg);
+    for (int64_t tile = tbeg; tile < tend; tile += tstep) {
       int64_t n = tile * kTM + ew * 32 + lane;
       bool valid = n < N;
       int k0 = 0, k1 = K;
@@ -385,7 +410,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         k1 = k0 + 1;
         valid = nn >= 0;
         n = valid ? nn : 0;
-        fetch(tile + gridDim.x);
+        fetch(tile + tstep);
       }
       const int g = (gid != nullptr && valid) ? gid[n] : 0;
       const float* lwg = lw + (size_t)g * K;
@@ -437,20 +462,20 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
     // thread <-> one point (TMEM lane); its 64 dims of K block kb stay in registers for the whole tile
     const int quad = warp & 3, kb = (warp - 8) >> 2;
     const int row = 32 * quad + lane;
-    uint32_t cnt = 0;
-    // list mode: the (cluster, row) of this thread are fetched two items ahead and the rows of the next item are
-    // prefetched into L2 while the current one is built (the gather is latency-bound otherwise)
-    int k_cur = 0, k_nx = 0;
-    int64_t n_cur = N, n_nx = N;
-    auto fetch = [&](int64_t it, int& kk, int64_t& nn) {
-      kk = 0;
-      nn = N;
-      if (it < ntiles) {
-        const int4 item = __ldg(items + it);
-        kk = item.x;
-        if (row < item.y) nn = (int64_t)__ldg(lrow + (((long long)(unsigned)item.z) | ((long long)item.w << 32)) + row);
-      }
+    uint32_t cnt = 0, bidx = 0;
+    int kprev = -1;
+    // List mode: the work items and the row indices travel ahead of the rows themselves, all with cp.async into
+    // the padding bytes of this warp's gather buffer, so that no lane ever waits on a dependent load:
+    //   while item t is built:  rows of item t+1, row indices of item t+2 and item t+3 are in flight.
+    // (A plain prefetch into registers stalls the warp at the first instruction that touches the loaded value --
+    // the address arithmetic of the next, dependent load -- for two global latencies per item.)
+    const uint32_t tbs_pad = sbase + kOffTrans + (uint32_t)(warp - 8) * kTransWarp + 256u;
+    auto item_slot = [&](int64_t t) { return tbs_pad + (uint32_t)(t % 3) * kTransRow; };
+    auto lrow_slot = [&](int64_t t) {
+      return tbs_pad + (uint32_t)(8 + 8 * (int)(t & 1) + (lane >> 2)) * kTransRow + 4u * (uint32_t)(lane & 3);
     };
+    auto item_base = [](const int4& it) { return ((long long)(unsigned)it.z) | ((long long)it.w << 32); };
+    int4 it0 = make_int4(-1, 0, 0, 0), it1 = it0;  // items t and t+1 (cluster -1: no such item)
     // Gathered rows (list mode): a thread reading its own row makes every load instruction touch 32 cache lines
     // (the L1 data pipe ran at 74 % and bounded the kernel, profiles/ncu_r01_refine_v4_raw.csv).  Instead the warp
     // copies two rows per instruction (16 lanes x 16 B each) into its private shared-memory buffer with cp.async, one
@@ -470,17 +495,30 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
     if constexpr (kList) {
-      fetch(blockIdx.x, k_cur, n_cur);
-      fetch((int64_t)blockIdx.x + gridDim.x, k_nx, n_nx);
-      gather_rows(n_cur);
+      // prologue with plain loads: items t0, t0+1 in registers, item t0+2 and the row indices of t0+1 in their slots
+      if (tbeg < tend) it0 = __ldg(items + tbeg);
+      if (tbeg + 1 < tend) it1 = __ldg(items + tbeg + 1);
+      const int64_t n0 = row < it0.y ? (int64_t)__ldg(lrow + item_base(it0) + row) : N;
+      if (row < it1.y) {
+        const int32_t r1 = __ldg(lrow + item_base(it1) + row);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(lrow_slot(tbeg + 1)), "r"(r1) : "memory");
+      }
+      if (lane == 0 && tbeg + 2 < tend) {
+        const int4 i2 = __ldg(items + tbeg + 2);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(item_slot(tbeg + 2)), "r"(i2.x), "r"(i2.y), "r"(i2.z), "r"(i2.w) : "memory");
+      }
+      gather_rows(n0);
     }
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t tile = tbeg; tile < tend; tile += tstep) {
       int64_t n = tile * kTM + row;
       int k0 = 0, k1 = K;
+      bool newk = true, lastk = true;
       if constexpr (kList) {
-        k0 = k_cur;
+        k0 = it0.x;
         k1 = k0 + 1;
-        n = n_cur;
+        newk = k0 != kprev;
+        kprev = k0;
+        lastk = it1.x != k0;  // the next item of this CTA (if any) uses another operand blob
       }
       float4 x[16];
       if constexpr (kList) {
@@ -491,11 +529,25 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = *reinterpret_cast<const float4*>(tb + lane * kTransRow + 16 * j);
+        // what arrived with the rows: the row index of item t+1 and item t+2
+        int64_t n1 = N;
+        if (row < it1.y) {
+          int32_t r1;
+          asm volatile("ld.shared.b32 %0, [%1];" : "=r"(r1) : "r"(lrow_slot(tile + 1)) : "memory");
+          n1 = r1;
+        }
+        int4 it2 = make_int4(-1, 0, 0, 0);
+        if (tile + 2 < tend)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(it2.x), "=r"(it2.y), "=r"(it2.z), "=r"(it2.w) : "r"(item_slot(tile + 2)) : "memory");
         __syncwarp();
-        k_cur = k_nx;
-        n_cur = n_nx;
-        fetch(tile + 2 * (int64_t)gridDim.x, k_nx, n_nx);
-        gather_rows(n_cur);
+        // next requests: item t+3, the row indices of item t+2, the rows of item t+1
+        if (lane == 0 && tile + 3 < tend)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(item_slot(tile + 3)), "l"(items + tile + 3) : "memory");
+        if (row < it2.y)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(lrow_slot(tile + 2)), "l"(lrow + item_base(it2) + row) : "memory");
+        gather_rows(n1);
+        it0 = it1;
+        it1 = it2;
       } else if (n < N) {
         const float4* src = reinterpret_cast<const float4*>(X + n * kD + 64 * kb);
 #pragma unroll
@@ -505,11 +557,12 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         for (int j = 0; j < 16; ++j) x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
       for (int k = k0; k < k1; ++k, ++cnt) {
-        const uint32_t bs = cnt % NS, bph = (cnt / NS) & 1;
+        if (newk) ++bidx;
+        const uint32_t bs = (bidx - 1) % NS, bph = ((bidx - 1) / NS) & 1;
         const uint32_t st = cnt & 1, ph = (cnt >> 1) & 1;
         const float sc = ascale[k];
         const float2 s2 = make_float2(sc, sc);
-        mbar_wait(bar(BB_FULL0 + bs), bph, err);
+        if (newk) mbar_wait(bar(BB_FULL0 + bs), bph, err);
         mbar_wait(bar(BA_EMPTY00 + 2 * st + kb), ph ^ 1, err);
         tc_fence_after();
         const float4* mh4 = reinterpret_cast<const float4*>(sgen + bs * kBBlob + kOffMean + 256 * kb);
@@ -540,7 +593,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar(BA_FULL00 + 2 * st + kb));
-          mbar_arrive(bar(BB_EMPTY0 + bs));
+          if (lastk) mbar_arrive(bar(BB_EMPTY0 + bs));
         }
       }
     }
@@ -558,10 +611,10 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 // sstat_tc128_kernel: centred scatter over the per-cluster lists of non-zero
 // responsibilities, D == 128:
 //     S_k += sum_r (x_r - c_k) q_r (x_r - c_k)^T ,   xs_k += sum_r q_r (x_r - c_k)
-// as a 128 x 128 x (rows) GEMM on tcgen05: A = s (X - c)^T [dims x rows] lives in
-// TMEM, B = q s (X - c) [dims x rows, rows contiguous] in swizzled shared memory,
-// both split into fp16 (hi, lo) with the three significant products accumulated in
-// fp32 TMEM accumulators.  s is a power of two that cannot saturate fp16 for any
+// as a 128 x 128 x (rows) GEMM on tcgen05 with both operands equal to
+// sqrt(q) s (X - c)^T [dims x rows]: A lives in TMEM, B (rows contiguous) in swizzled
+// shared memory, split into fp16 (hi, lo) with the three significant products
+// accumulated in fp32 TMEM accumulators.  s is a power of two that cannot saturate fp16 for any
 // row of the data set (engine: 2^14 / max|x - c|).  A builder thread owns one
 // dimension (= TMEM lane = B row) and 64 of the 128 rows of a tile; rows are
 // gathered from X through the (row, q) lists.
@@ -677,7 +730,7 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
             int2 v = make_int2(-1, 0);
             if (l < w.l1) {
               v.x = lrow[w.base + l];
-              v.y = __float_as_int(lq[w.base + l]);
+              v.y = __float_as_int(sqrtf(lq[w.base + l]));  // the builders work with sqrt(q), see below
             }
             dst[e * 32 + lane] = v;
           }
@@ -810,21 +863,21 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
             uint32_t bh[4], bl[4];
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
+              // S_k = sum_r (w a)(w a)^T with w = sqrt(q): both MMA operands are the same numbers (A in TMEM, B in
+              // shared memory), so one scaling and one fp16 hi/lo split serve both
               const int r = 32 * g + 8 * c + 2 * p;
               const int2 e0 = lst[r], e1 = lst[r + 1];
-              const float q0 = __int_as_float(e0.y), q1 = __int_as_float(e1.y);
-              const float a0 = e0.x >= 0 ? fmaf(a[r], scale, ncs) : 0.f;
-              const float a1 = e1.x >= 0 ? fmaf(a[r + 1], scale, ncs) : 0.f;
+              const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
+              const float a0 = e0.x >= 0 ? w0 * fmaf(a[r], scale, ncs) : 0.f;
+              const float a1 = e1.x >= 0 ? w1 * fmaf(a[r + 1], scale, ncs) : 0.f;
               const uint32_t hh = pack_f16x2_sat(a0, a1);
               const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+              const uint32_t ll = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
               ah[4 * c + p] = hh;
-              al[4 * c + p] = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
-              const float v0 = q0 * a0, v1 = q1 * a1;
-              xs32 += v0 + v1;
-              const uint32_t vh = pack_f16x2_sat(v0, v1);
-              const float2 vf = __half22float2(*reinterpret_cast<const __half2*>(&vh));
-              bh[p] = vh;
-              bl[p] = pack_f16x2_sat(v0 - vf.x, v1 - vf.y);
+              al[4 * c + p] = ll;
+              bh[p] = hh;
+              bl[p] = ll;
+              xs32 = fmaf(w0, a0, fmaf(w1, a1, xs32));
             }
             const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
@@ -1691,15 +1744,52 @@ cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t*
 // i >= d, split into fp16 hi/lo and laid out exactly as the kernel's shared
 // memory expects (row pitch 128 B = 64 fp16 of one K block, 16-byte chunks
 // XOR-swizzled with row % 8; K block 1 stores rows 64..127 only).
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__)
+// eight consecutive K entries of one row are one 16-byte chunk of the swizzled layout: convert them with F16C
+__attribute__((target("avx2,f16c"))) static void pack_rows_f16c(const double* R, double bscale, uint8_t* out) {
+  for (int kbk = 0; kbk < 2; ++kbk) {
+    const uint32_t base_hi = kbk == 0 ? 0u : 2 * kAPart;
+    const uint32_t base_lo = base_hi + (kbk == 0 ? kAPart : kAPart / 2);
+    for (int i = 64 * kbk; i < 128; ++i) {
+      const int r = i - 64 * kbk;
+      for (int ch = 0; ch < 8; ++ch) {
+        const int d0 = 64 * kbk + 8 * ch;
+        if (d0 > i) break;
+        float v[8];
+        for (int e = 0; e < 8; ++e) v[e] = d0 + e <= i ? (float)(R[(size_t)i * 128 + d0 + e] * bscale) : 0.f;
+        const __m256 x = _mm256_loadu_ps(v);
+        const __m128i h = _mm256_cvtps_ph(x, _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+        const __m256 back = _mm256_cvtph_ps(h);
+        const __m128i l = _mm256_cvtps_ph(_mm256_sub_ps(x, back), _MM_FROUND_TO_NEAREST_INT | _MM_FROUND_NO_EXC);
+        const uint32_t off = (uint32_t)r * 128u + (((uint32_t)ch ^ ((uint32_t)r & 7u)) << 4);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + base_hi + off), h);
+        _mm_storeu_si128(reinterpret_cast<__m128i*>(out + base_lo + off), l);
+      }
+    }
+  }
+}
+static bool have_f16c() {
+  static const bool ok = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("f16c");
+  return ok;
+}
+#else
+static bool have_f16c() { return false; }
+static void pack_rows_f16c(const double*, double, uint8_t*) {}
+#endif
+
 void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */, double bscale,
                      const double* mean_rel /* [128] cluster mean minus the data centre */, double ascale, uint8_t* out) {
-  for (uint32_t i = 0; i < kBBlob; ++i) out[i] = 0;
+  std::memset(out, 0, kBBlob);
   float* mh = reinterpret_cast<float*>(out + kOffMean);
   float* nl = mh + 128;
   for (int d = 0; d < 128; ++d) {
     const float hi = (float)mean_rel[d];
     mh[d] = hi;
     nl[d] = (float)(-(mean_rel[d] - (double)hi) * ascale);
+  }
+  if (have_f16c()) {
+    pack_rows_f16c(R, bscale, out);
+    return;
   }
   for (int kbk = 0; kbk < 2; ++kbk) {
     const uint32_t base_hi = kbk == 0 ? 0u : 2 * kAPart;
