@@ -332,7 +332,9 @@ def main():
         # two-level E pass: level 1 evaluates all K*D^2 algorithmic flops of every point (one fp16 product, rigorous
         # bound); levels 2-3 only touch the candidate pairs.  The dominant kernel is level 1.
         kname, kms = "estep_coarse_tc128_kernel", coarse_ms / a.steps
-        traffic = None
+        # ncu --set full at N=4M (profiles/ncu_r01_coarse_v4_raw.csv): dram read 2.12 GB + write 1.07 GB per launch
+        # = 799 B / point (algorithmic: 512 B of X, 256 B of level-1 bounds, 8 B of candidate mask)
+        traffic = 799.0 * nloc
         levels = {k_: (lv[k_] / a.steps) for k_ in ("coarse_ms", "lists_ms", "refine_ms", "finalize_ms")}
         levels["candidate_pairs_per_row"] = lv["pairs"] / a.steps / max(nloc, 1)
     elif e_ms >= s_ms:
