@@ -27,6 +27,7 @@ struct NcclId { char internal[128]; };
 typedef int (*fn_get_id)(NcclId*);
 typedef int (*fn_init_rank)(void**, int, NcclId, int);
 typedef int (*fn_allreduce)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*fn_allgather)(const void*, void*, size_t, int, void*, cudaStream_t);
 typedef int (*fn_destroy)(void*);
 typedef const char* (*fn_errstr)(int);
 struct NcclApi {
@@ -34,6 +35,7 @@ struct NcclApi {
   fn_get_id get_id = nullptr;
   fn_init_rank init_rank = nullptr;
   fn_allreduce allreduce = nullptr;
+  fn_allgather allgather = nullptr;
   fn_destroy destroy = nullptr;
   fn_errstr errstr = nullptr;
   bool ok = false;
@@ -50,6 +52,7 @@ NcclApi& nccl() {
       api.get_id = (fn_get_id)dlsym(api.h, "ncclGetUniqueId");
       api.init_rank = (fn_init_rank)dlsym(api.h, "ncclCommInitRank");
       api.allreduce = (fn_allreduce)dlsym(api.h, "ncclAllReduce");
+      api.allgather = (fn_allgather)dlsym(api.h, "ncclAllGather");
       api.destroy = (fn_destroy)dlsym(api.h, "ncclCommDestroy");
       api.errstr = (fn_errstr)dlsym(api.h, "ncclGetErrorString");
       api.ok = api.get_id && api.init_rank && api.allreduce && api.destroy;
@@ -57,7 +60,7 @@ NcclApi& nccl() {
   }
   return api;
 }
-const int kNcclDouble = 8, kNcclSum = 0;
+const int kNcclDouble = 8, kNcclSum = 0, kNcclUint8 = 1;
 }  // namespace
 
 int nccl_get_unique_id(char out[128], std::string* err) {
@@ -223,6 +226,16 @@ void Engine::comm_init_host(HostAllreduceFn fn, void* ctx, int rank, int world) 
 // One process per GPU on one box: every rank runs the same replicated host-side updates, so the ranks share the
 // cores instead of each starting hardware_concurrency() threads.
 void Engine::share_host_threads() {
+  // With NCCL the ranks also split the O(K D^3) half of the M step and the operand packing instead of repeating them
+  // (iteration(), ephase_tc()); LCB_DIST_MSTEP=0 keeps the replicated form.
+  // The factor exchange moves 8 (1 + D^2) K bytes through the host each iteration, which pays from four ranks
+  // on; LCB_DIST_MSTEP=0 keeps everything replicated, =1 splits the factorisations for any world size.
+  dist_mstep_ = world_ > 1 && nccl_comm_ != nullptr && nccl().allgather != nullptr;
+  dist_factor_ = dist_mstep_ && world_ >= 4;
+  if (const char* dm = std::getenv("LCB_DIST_MSTEP")) {
+    if (dm[0] == '0') dist_mstep_ = dist_factor_ = false;
+    if (dm[0] == '1') dist_factor_ = dist_mstep_;
+  }
   if (std::getenv("LCB_HOST_THREADS") != nullptr || world_ <= 1) return;
   const int hw = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
   host_threads_ = std::max(2, hw / std::min(world_, 8));
@@ -916,6 +929,9 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     cbar += cc[k];
   }
   cbar /= K;
+  // ranks pack contiguous blocks of the operand blobs and all-gather them on the device (K % world == 0)
+  const bool split_pack = dist_mstep_ && K % world_ == 0 && K >= world_ && &v == &main_;
+  const int own0 = split_pack ? K / world_ * rank_ : 0, own1 = split_pack ? K / world_ * (rank_ + 1) : K;
   // level-1 operand scale: s_g max|x| <= 2^8 keeps fp16(s_g x) far from saturation and its small entries normal
   const double xspan = std::max(xabs_max_, 1e-30);
   const double sg = std::ldexp(1.0, std::min(100, std::max(-100, (int)std::floor(std::log2(256.0 / xspan)))));
@@ -940,7 +956,8 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     const std::vector<double>& m = clusters[k].mean();
     std::vector<double> rel(D);
     for (int d = 0; d < D; ++d) rel[d] = m[d] - centre_[d];
-    dev::tc_pack_cluster(R.data(), t / s, rel.data(), s, h + (size_t)k * dev::kTcBlobBytes);
+    if (!split_pack || (k >= own0 && k < own1))
+      dev::tc_pack_cluster(R.data(), t / s, rel.data(), s, h + (size_t)k * dev::kTcBlobBytes);
     h_as[k] = (float)s;
     h_it2[k] = (float)(1.0 / (t * t));
     h_chat[k] = (float)(cc[k] - cbar);
@@ -990,6 +1007,12 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
   }
   reserve(d_tc_, total);
   check(cudaMemcpyAsync(d_tc_.p, h, total, cudaMemcpyHostToDevice, stream_), "H2D tc params");
+  if (split_pack) {
+    const size_t chunk = (size_t)(K / world_) * dev::kTcBlobBytes;
+    const int rc = nccl().allgather((const unsigned char*)d_tc_.p + chunk * (size_t)rank_, d_tc_.p, chunk, kNcclUint8,
+                                    nccl_comm_, stream_);
+    if (rc != 0) throw Error{4, "ncclAllGather failed"};
+  }
   const uint8_t* d_blob = (const uint8_t*)d_tc_.p;
   const float* df = reinterpret_cast<const float*>(d_blob + off_f);
   const float* d_as = df;
@@ -1181,13 +1204,19 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
   for (int k = 0; k < K; ++k) clusters[k].clearobs();
   sphase(v, weights, clusters, centres);
   // VBM for the clusters (cluster.cpp:215-217 runs this loop under OpenMP as well)
+  const bool split_factor = dist_factor_ && ckind_ == kGaussWish && K >= world_ && &v == &main_;
   {
     int bad = 0;
     Error first{0, ""};
 #pragma omp parallel for schedule(dynamic) num_threads(host_threads_) if (K >= 8)
     for (int k = 0; k < K; ++k) {
       try {
-        clusters[k].update();
+        if (!split_factor) {
+          clusters[k].update();
+        } else {
+          clusters[k].update_params();
+          if (k % world_ == rank_) clusters[k].factor();
+        }
       } catch (const Error& e) {
 #pragma omp critical
         if (!bad) {
@@ -1195,6 +1224,28 @@ void Engine::iteration(View& v, std::vector<WeightPost>& weights, std::vector<Cl
           first = e;
         }
       }
+    }
+    if (split_factor) {
+      // every rank factorised K / world of the matrices: exchange {log det, L^-1} (zero elsewhere, summed), and the
+      // failure count so that all ranks raise the same error
+      const size_t per = 1 + (size_t)D * D, n = (size_t)K * per + 1;
+      double* buf = (double*)pinned(sizeof(double) * n);
+      std::memset(buf, 0, sizeof(double) * n);
+      if (!bad)
+        for (int k = rank_; k < K; k += world_) clusters[k].export_factor(buf + (size_t)k * per);
+      buf[n - 1] = bad ? 1.0 : 0.0;
+      reserve(d_tmp_, sizeof(double) * n);
+      check(cudaMemcpyAsync(d_tmp_.p, buf, sizeof(double) * n, cudaMemcpyHostToDevice, stream_), "H2D factors");
+      allreduce((double*)d_tmp_.p, (int64_t)n);
+      check(cudaMemcpyAsync(buf, d_tmp_.p, sizeof(double) * n, cudaMemcpyDeviceToHost, stream_), "D2H factors");
+      sync();
+      if (buf[n - 1] > 0 && !bad) {
+        bad = 1;
+        first = Error{3, "Matrix A is not positive definite."};
+      }
+      if (!bad)
+        for (int k = 0; k < K; ++k)
+          if (k % world_ != rank_) clusters[k].import_factor(buf + (size_t)k * per);
     }
     if (bad) throw first;
   }

@@ -115,6 +115,8 @@ class Engine {
   // Two-level E step (one-product distances for all pairs, exact logits for the candidates only).
   // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
   bool use_two_level_ = true;
+  bool dist_mstep_ = false;     // ranks share the operand packing (NCCL only) ...
+  bool dist_factor_ = false;    // ... and the factorisations of the M step
   int host_threads_ = 1;        // threads of the host-side posterior updates (engine.cu)
   int tc_stage_ = 0;            // 0 full, 1 stop after level 1, 2 stop after level 2
   int two_level_skip_ = 0;      // iterations left before the two-level path is tried again after it did not pay

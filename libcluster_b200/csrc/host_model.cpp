@@ -271,6 +271,21 @@ void ClusterPost::factor() {
 }
 
 void ClusterPost::update() {
+  update_params();
+  if (kind_ == kGaussWish) factor();
+}
+
+void ClusterPost::export_factor(double* out) const {
+  out[0] = logdW_;
+  std::memcpy(out + 1, Linv_.data(), sizeof(double) * (size_t)D_ * D_);
+}
+
+void ClusterPost::import_factor(const double* in) {
+  logdW_ = in[0];
+  Linv_.assign(in + 1, in + 1 + (size_t)D_ * D_);
+}
+
+void ClusterPost::update_params() {
   const int D = D_;
   std::vector<double> xbar(D, 0.0);
   if (N_s_ > 0)
@@ -287,7 +302,6 @@ void ClusterPost::update() {
         iW_[(size_t)i * D + j] = iW_p_[(size_t)i * D + j] + (xx_s_[(size_t)i * D + j] - xbar[i] * x_s_[j]) +
                                  w * di * (xbar[j] - m_p_[j]);
     }
-    factor();
   } else {
     nu_ = nu_p_ + N_ / 2;
     bool bad = false;

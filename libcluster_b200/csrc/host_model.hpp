@@ -70,6 +70,13 @@ class ClusterPost {
   // raw statistics.
   void add_centred_stats(double n, const double* s, const double* S, const double* c);
   void update();  // throws Error (domain / invalid) like the reference
+  // The two halves of update() for a GaussWish, so that ranks can share the O(D^3) half: update_params() is
+  // everything up to and including iW; factor() the Cholesky of iW and its inverse (throws if iW is not positive
+  // definite); export_factor / import_factor move {logdW, L^-1} (1 + D*D doubles) between ranks.
+  void update_params();
+  void factor();
+  void export_factor(double* out) const;
+  void import_factor(const double* in);
   double fenergy() const;
   double getN() const { return N_; }
   double getprior() const { return prior_; }
@@ -95,7 +102,6 @@ class ClusterPost {
   void split_direction(std::vector<double>& v) const;
 
  private:
-  void factor();  // Cholesky of iW and its inverse (GaussWish)
   int kind_, D_;
   double prior_, N_;
   double nu_p_, beta_p_, logdW_p_, F_p_;
