@@ -942,9 +942,10 @@ double Engine::ephase_tc(View& v, const std::vector<WeightPost>& weights, const 
     std::vector<double> R;
     clusters[k].whitener(R);
     // a = s (x - m): s maps the widest posterior standard deviation to ~32
-    const std::vector<double> cov = clusters[k].cov();
+    // widest posterior variance = largest diagonal entry of cov() = iW / nu
+    const std::vector<double>& iW = clusters[k].iW();
     double cvmax = 0, rmax = 0;
-    for (int d = 0; d < D; ++d) cvmax = std::max(cvmax, cov[(size_t)d * D + d]);
+    for (int d = 0; d < D; ++d) cvmax = std::max(cvmax, iW[(size_t)d * D + d] / clusters[k].nu());
     for (size_t i = 0; i < R.size(); ++i) rmax = std::max(rmax, std::fabs(R[i]));
     int es_ = (int)std::lround(std::log2(32.0 / std::sqrt(std::max(cvmax, 1e-300))));
     es_ = std::min(60, std::max(-60, es_));
