@@ -367,7 +367,7 @@ def main():
             e2e = {"value": None, "unit": "points/s", "error": str(ex)[:200]}
 
     cpu = None
-    if rank == 0 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:   # reported at N=1 only; the other ranks would idle in NCCL teardown
         rows, times, kind, cores = cpu_iteration_rate(D, K, budget_s=15.0, reps=1)
         cpu = {"value": rows / times[0], "unit": "points/s", "cores": cores, "kind": kind,
                "sample": "%d rows of the same synthetic mixture, one vbem iteration (fp64; %s)" % (
