@@ -124,6 +124,9 @@ int lcb_get_step_timing(lcb_engine *e, double out[4]);
 int lcb_get_estep_detail(lcb_engine *e, double out[8]);
 /* The CUDA stream all engine work is issued on (cudaStream_t as void*). */
 void *lcb_stream(lcb_engine *e);
+/* Host-only self-test (no device needed): the operand packing has a run-time-dispatched F16C path; returns the number
+ * of bytes in which it differs from the portable path on a test matrix (0 = identical, also where F16C is absent). */
+int lcb_selftest_host_packing(void);
 
 /* ---- multi-GPU: rows sharded over ranks, one all-reduce of the packed
  * sufficient statistics per VB iteration.  No reference

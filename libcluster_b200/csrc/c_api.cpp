@@ -8,6 +8,7 @@
 
 #include "../../include/libcluster_b200.h"
 #include "engine.hpp"
+#include "tc_kernels.cuh"
 #include "host_model.hpp"
 
 using namespace lcb;
@@ -138,6 +139,7 @@ int lcb_get_estep_detail(lcb_engine* e, double out[8]) {
   return LCB_OK;
 }
 void* lcb_stream(lcb_engine* e) { return e ? (void*)e->e->stream() : nullptr; }
+int lcb_selftest_host_packing(void) { return lcb::dev::tc_pack_selftest(); }
 
 int lcb_nccl_unique_id(char out[128]) {
   std::string err;

@@ -35,6 +35,7 @@
 #include "tc_kernels.cuh"
 
 #include <cstring>
+#include <vector>
 
 #if defined(__x86_64__) && defined(__GNUC__)
 #include <immintrin.h>
@@ -1777,6 +1778,31 @@ static bool have_f16c() { return false; }
 static void pack_rows_f16c(const double*, double, uint8_t*) {}
 #endif
 
+static bool g_pack_force_scalar = false;
+
+// Packs one operand with the F16C path and with the portable path; returns the number of differing bytes (0 where
+// F16C is not available: there is only one path then).
+int tc_pack_selftest() {
+  std::vector<double> R((size_t)128 * 128, 0.0), rel(128);
+  uint64_t st = 0x9e3779b97f4a7c15ull;
+  auto rnd = [&]() {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    return (double)(int64_t)(st >> 11) / 9007199254740992.0 * 2.0 - 1.0;
+  };
+  for (int i = 0; i < 128; ++i) {
+    rel[i] = 3.0 * rnd();
+    for (int j = 0; j <= i; ++j) R[(size_t)i * 128 + j] = std::ldexp(rnd(), (int)(8.0 * rnd()));  // wide dynamic range
+  }
+  std::vector<uint8_t> a(kBBlob), b(kBBlob);
+  tc_pack_cluster(R.data(), 37.5, rel.data(), 0.25, a.data());
+  g_pack_force_scalar = true;
+  tc_pack_cluster(R.data(), 37.5, rel.data(), 0.25, b.data());
+  g_pack_force_scalar = false;
+  int diff = 0;
+  for (uint32_t i = 0; i < kBBlob; ++i) diff += a[i] != b[i];
+  return diff;
+}
+
 void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */, double bscale,
                      const double* mean_rel /* [128] cluster mean minus the data centre */, double ascale, uint8_t* out) {
   std::memset(out, 0, kBBlob);
@@ -1787,7 +1813,7 @@ void tc_pack_cluster(const double* R /* [128][128] row-major lower-triangular */
     mh[d] = hi;
     nl[d] = (float)(-(mean_rel[d] - (double)hi) * ascale);
   }
-  if (have_f16c()) {
+  if (have_f16c() && !g_pack_force_scalar) {
     pack_rows_f16c(R, bscale, out);
     return;
   }

@@ -59,6 +59,7 @@ cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t*
                         const float* cen, float scale, double* xs, double* S, unsigned* err);
 
 void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
+int tc_pack_selftest();  // bytes differing between the F16C and the portable packing of one operand
 
 }  // namespace dev
 }  // namespace lcb

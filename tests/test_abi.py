@@ -24,6 +24,11 @@ def test_every_declared_symbol_is_exported():
     assert b"sm_100a" in L.lcb_version()
 
 
+def test_operand_packing_paths_agree():
+    """tc_pack_cluster picks an F16C path at run time; it must produce the bytes of the portable path."""
+    assert nat.lib().lcb_selftest_host_packing() == 0
+
+
 def test_no_gpu_means_error_not_fallback():
     if nat.lib().lcb_device_count() > 0:
         pytest.skip("a GPU is visible")
