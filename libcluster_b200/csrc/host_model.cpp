@@ -133,44 +133,70 @@ double WeightPost::fenergy() const {
 // ------------------------------------------------------------ dense helpers --
 // The two O(D^3) routines of the host M step.  Their inner loops run along rows; each exists in a baseline build and
 // in an AVX2+FMA build chosen at run time (the library itself is compiled for generic x86-64).
-#define LCB_CHOLESKY_BODY                                            \
-  for (int j = 0; j < D; ++j) {                                      \
-    double* rj = A + (size_t)j * D;                                  \
-    double d = rj[j];                                                \
-    for (int p = 0; p < j; ++p) d -= rj[p] * rj[p];                  \
-    if (!(d > 0.0)) return false;                                    \
-    d = std::sqrt(d);                                                \
-    rj[j] = d;                                                       \
-    const double invd = 1.0 / d;                                     \
-    for (int i = j + 1; i < D; ++i) {                                \
-      double* ri = A + (size_t)i * D;                                \
-      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;                         \
-      int p = 0;                                                     \
-      for (; p + 4 <= j; p += 4) {                                   \
-        t0 += ri[p] * rj[p];                                         \
-        t1 += ri[p + 1] * rj[p + 1];                                 \
-        t2 += ri[p + 2] * rj[p + 2];                                 \
-        t3 += ri[p + 3] * rj[p + 3];                                 \
-      }                                                              \
-      for (; p < j; ++p) t0 += ri[p] * rj[p];                        \
-      ri[j] = (ri[j] - ((t0 + t1) + (t2 + t3))) * invd;              \
-    }                                                                \
-    for (int c = j + 1; c < D; ++c) rj[c] = 0.0;                     \
-  }                                                                  \
+#define LCB_CHOLESKY_BODY                                                        \
+  for (int j = 0; j < D; ++j) {                                                  \
+    double* rj = A + (size_t)j * D;                                              \
+    double d = rj[j];                                                            \
+    for (int p = 0; p < j; ++p) d -= rj[p] * rj[p];                              \
+    if (!(d > 0.0)) return false;                                                \
+    d = std::sqrt(d);                                                            \
+    rj[j] = d;                                                                   \
+    const double invd = 1.0 / d;                                                 \
+    int i = j + 1;                                                               \
+    /* four rows at a time share the loads of row j */                           \
+    for (; i + 4 <= D; i += 4) {                                                 \
+      double* r0 = A + (size_t)i * D;                                            \
+      double* r1 = r0 + D;                                                       \
+      double* r2 = r1 + D;                                                       \
+      double* r3 = r2 + D;                                                       \
+      double t0 = 0, t1 = 0, t2 = 0, t3 = 0;                                     \
+      for (int p = 0; p < j; ++p) {                                              \
+        const double x = rj[p];                                                  \
+        t0 += r0[p] * x;                                                         \
+        t1 += r1[p] * x;                                                         \
+        t2 += r2[p] * x;                                                         \
+        t3 += r3[p] * x;                                                         \
+      }                                                                          \
+      r0[j] = (r0[j] - t0) * invd;                                               \
+      r1[j] = (r1[j] - t1) * invd;                                               \
+      r2[j] = (r2[j] - t2) * invd;                                               \
+      r3[j] = (r3[j] - t3) * invd;                                               \
+    }                                                                            \
+    for (; i < D; ++i) {                                                         \
+      double* ri = A + (size_t)i * D;                                            \
+      double t = 0;                                                              \
+      for (int p = 0; p < j; ++p) t += ri[p] * rj[p];                            \
+      ri[j] = (ri[j] - t) * invd;                                                \
+    }                                                                            \
+    for (int c = j + 1; c < D; ++c) rj[c] = 0.0;                                 \
+  }                                                                              \
   return true;
 
-#define LCB_INVERT_BODY                                              \
-  for (int i = 0; i < D; ++i) {                                      \
-    double* ri = Li + (size_t)i * D;                                 \
-    const double* li = L + (size_t)i * D;                            \
-    for (int p = 0; p < i; ++p) {                                    \
-      const double f = li[p];                                        \
-      const double* rp = Li + (size_t)p * D;                         \
-      for (int c = 0; c <= p; ++c) ri[c] -= f * rp[c];               \
-    }                                                                \
-    const double inv = 1.0 / li[i];                                  \
-    for (int c = 0; c < i; ++c) ri[c] *= inv;                        \
-    ri[i] = inv;                                                     \
+#define LCB_INVERT_BODY                                                          \
+  for (int i = 0; i < D; ++i) {                                                  \
+    double* ri = Li + (size_t)i * D;                                             \
+    const double* li = L + (size_t)i * D;                                        \
+    int p = 0;                                                                   \
+    /* four rows of L^-1 at a time share the update of row i */                  \
+    for (; p + 4 <= i; p += 4) {                                                 \
+      const double f0 = li[p], f1 = li[p + 1], f2 = li[p + 2], f3 = li[p + 3];   \
+      const double* q0 = Li + (size_t)p * D;                                     \
+      const double* q1 = q0 + D;                                                 \
+      const double* q2 = q1 + D;                                                 \
+      const double* q3 = q2 + D;                                                 \
+      for (int c = 0; c <= p; ++c) ri[c] -= f0 * q0[c] + f1 * q1[c] + f2 * q2[c] + f3 * q3[c]; \
+      ri[p + 1] -= f1 * q1[p + 1] + f2 * q2[p + 1] + f3 * q3[p + 1];             \
+      ri[p + 2] -= f2 * q2[p + 2] + f3 * q3[p + 2];                              \
+      ri[p + 3] -= f3 * q3[p + 3];                                               \
+    }                                                                            \
+    for (; p < i; ++p) {                                                         \
+      const double f = li[p];                                                    \
+      const double* rp = Li + (size_t)p * D;                                     \
+      for (int c = 0; c <= p; ++c) ri[c] -= f * rp[c];                           \
+    }                                                                            \
+    const double inv = 1.0 / li[i];                                              \
+    for (int c = 0; c < i; ++c) ri[c] *= inv;                                    \
+    ri[i] = inv;                                                                 \
   }
 
 static bool cholesky_generic(double* A, int D) { LCB_CHOLESKY_BODY }
