@@ -55,7 +55,7 @@ def test_weight_posteriors(kind, cls, K):
 
 
 @pytest.mark.parametrize("kind,cls", [(po.C_GAUSSWISH, lc.GaussWish), (po.C_NORMGAMMA, lc.NormGamma)])
-@pytest.mark.parametrize("D", [1, 2, 7, 32])
+@pytest.mark.parametrize("D", [1, 2, 7, 13, 32, 128])
 def test_cluster_posteriors_from_stats(kind, cls, D):
     rng = np.random.default_rng(D)
     X = rng.normal(size=(300, D)) * 1.7 - 4
