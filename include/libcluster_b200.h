@@ -127,6 +127,15 @@ void *lcb_stream(lcb_engine *e);
 /* Host-only self-test (no device needed): the operand packing has a run-time-dispatched F16C path; returns the number
  * of bytes in which it differs from the portable path on a test matrix (0 = identical, also where F16C is absent). */
 int lcb_selftest_host_packing(void);
+/* Counters of the last lcb_vbem_step: out[0] kernel launches, out[1] collectives (NCCL or host callback),
+ * out[2] host synchronisations inside the step, out[3] 1 when the M step ran on the device (default; the
+ * environment variable LCB_HOST_MSTEP=1 keeps the posterior updates of cluster.cpp:211,217 on the host). */
+int lcb_get_step_counts(lcb_engine *e, double out[4]);
+/* Host-only self-test: the device M step orders the sticks of StickBreak / GDirichlet (distributions.cpp:146) with a
+ * restatement of libstdc++'s std::sort so that exact ties fall as in the reference; order[] receives the indices of
+ * counts[] sorted greater-first by that code; the return value is the number of positions in which it differs from
+ * std::sort on the same input (0 = identical order). */
+int lcb_selftest_stick_order(const double *counts, int n, int *order);
 
 /* ---- multi-GPU: rows sharded over ranks, one all-reduce of the packed
  * sufficient statistics per VB iteration.  No reference

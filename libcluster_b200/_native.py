@@ -50,6 +50,8 @@ SIGNATURES = {
     "lcb_get_estep_detail": (C.c_int, [_vp, _dp]),
     "lcb_stream": (_vp, [_vp]),
     "lcb_selftest_host_packing": (C.c_int, []),
+    "lcb_get_step_counts": (C.c_int, [_vp, _dp]),
+    "lcb_selftest_stick_order": (C.c_int, [_dp, C.c_int, _ip]),
     "lcb_nccl_unique_id": (C.c_int, [C.c_char_p]),
     "lcb_comm_init_nccl": (C.c_int, [_vp, C.c_char_p, C.c_int, C.c_int]),
     "lcb_comm_init_host": (C.c_int, [_vp, ALLREDUCE_FN, _vp, C.c_int, C.c_int]),

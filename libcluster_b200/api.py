@@ -139,6 +139,13 @@ class Engine:
         nat.check(nat.lib().lcb_get_step_timing(self._h, _dp(out)))
         return dict(sstat_ms=out[0], estep_ms=out[1], step_ms=out[2], launches=int(out[3]))
 
+    def step_counts(self):
+        """Launches, collectives and host synchronisations of the last vbem_step; device_mstep tells whether the
+        posterior updates ran on the GPU (default) or on the host (LCB_HOST_MSTEP=1)."""
+        out = np.zeros(4)
+        nat.check(nat.lib().lcb_get_step_counts(self._h, _dp(out)))
+        return dict(launches=int(out[0]), collectives=int(out[1]), host_syncs=int(out[2]), device_mstep=bool(out[3]))
+
     def estep_detail(self):
         """Break-down of the last tensor-core E pass (lcb_get_estep_detail)."""
         out = np.zeros(8)

@@ -16,7 +16,7 @@ LIB = os.path.join(OUT_DIR, "liblcb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fopenmp,-Wall,-Wno-unused-function"]
-SOURCES = ["kernels.cu", "tc_kernels.cu", "engine.cu", "host_model.cpp", "c_api.cpp"]
+SOURCES = ["kernels.cu", "tc_kernels.cu", "mstep.cu", "engine.cu", "engine_dev.cu", "host_model.cpp", "c_api.cpp"]
 
 
 def _newer(src, obj):
@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
     for s in SOURCES:
         src = os.path.join(CSRC, s)
         if not os.path.exists(src):
-            continue
+            raise FileNotFoundError(src)
         obj = os.path.join(OUT_DIR, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
         if force or _newer(src, obj):

@@ -1,7 +1,10 @@
 // c_api.cpp -- extern "C" boundary declared in include/libcluster_b200.h.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstring>
+#include <utility>
+#include <vector>
 #include <exception>
 #include <new>
 #include <string>
@@ -9,6 +12,7 @@
 #include "../../include/libcluster_b200.h"
 #include "engine.hpp"
 #include "tc_kernels.cuh"
+#include "mstep.cuh"
 #include "host_model.hpp"
 
 using namespace lcb;
@@ -140,6 +144,23 @@ int lcb_get_estep_detail(lcb_engine* e, double out[8]) {
 }
 void* lcb_stream(lcb_engine* e) { return e ? (void*)e->e->stream() : nullptr; }
 int lcb_selftest_host_packing(void) { return lcb::dev::tc_pack_selftest(); }
+int lcb_get_step_counts(lcb_engine* e, double out[4]) {
+  if (!e || !out) return bad("null argument");
+  e->e->get_step_counts(out);
+  return LCB_OK;
+}
+int lcb_selftest_stick_order(const double* counts, int n, int* order) {
+  if (!counts || !order || n < 0) return bad("null argument");
+  lcb::dev::sort_desc_like_std(counts, n, order);
+  // the reference's own call (distributions.cpp:146): std::sort on (index, count) pairs, greater count first
+  std::vector<std::pair<int, double>> ov((size_t)n);
+  for (int k = 0; k < n; ++k) ov[(size_t)k] = std::make_pair(k, counts[k]);
+  std::sort(ov.begin(), ov.end(),
+            [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.second > b.second; });
+  int diff = 0;
+  for (int k = 0; k < n; ++k) diff += ov[(size_t)k].first != order[k];
+  return diff;
+}
 
 int lcb_nccl_unique_id(char out[128]) {
   std::string err;

@@ -83,7 +83,10 @@ int nccl_get_unique_id(char out[128], std::string* err) {
 void Engine::check(cudaError_t e, const char* what) const {
   if (e != cudaSuccess) throw Error{4, std::string(what) + ": " + cudaGetErrorString(e)};
 }
-void Engine::sync() { check(cudaStreamSynchronize(stream_), "stream synchronize"); }
+void Engine::sync() {
+  ++syncs_;
+  check(cudaStreamSynchronize(stream_), "stream synchronize");
+}
 
 Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   if (precision != kF32 && precision != kF64) throw_invalid("precision must be LCB_F32 or LCB_F64");
@@ -113,16 +116,20 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
     if (std::strcmp(sg, "coarse") == 0) tc_stage_ = 1;
     else if (std::strcmp(sg, "refine") == 0) tc_stage_ = 2;
   }
+  if (const char* hm = std::getenv("LCB_HOST_MSTEP")) use_dev_mstep_ = !(hm[0] && hm[0] != '0');
+  check(cudaMallocHost((void**)&h_iter_, sizeof(double) * 64), "cudaMallocHost");
 }
 
 Engine::~Engine() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
   free_view(main_);
-  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_, &d_cmask_, &d_items_};
+  DeviceBuf* bufs[] = {&d_RT_, &d_mhi_, &d_mlo_, &d_chat_, &d_lw_, &d_act_, &d_cen_, &d_stats_, &d_small_, &d_tmp_, &d_mean_, &d_tc_, &d_nzcnt_, &d_nzoff_, &d_list_, &d_err_, &d_cmask_, &d_items_,
+                       &d_raw_, &d_post_, &d_work_, &d_iter_, &d_centre_, &d_wscr_, &d_vaug_};
   for (DeviceBuf* b : bufs)
     if (b->p) cudaFree(b->p);
   if (h_pin_) cudaFreeHost(h_pin_);
+  if (h_iter_) cudaFreeHost(h_iter_);
   for (auto& e : ev_)
     if (e) cudaEventDestroy(e);
   if (nccl_comm_ && nccl().ok) nccl().destroy(nccl_comm_);
@@ -158,6 +165,10 @@ void* Engine::pinned(size_t bytes) {
 
 void Engine::free_view(View& v) {
   list_valid_ = false;
+  if (dev_view_ == &v) {
+    dev_live_ = false;
+    host_stale_ = false;
+  }
   if (v.owns_x && v.X) cudaFree(v.X);
   if (v.owns_x && v.gid) cudaFree(v.gid);
   if (v.q) cudaFree(v.q);
@@ -241,8 +252,29 @@ void Engine::share_host_threads() {
   host_threads_ = std::max(2, hw / std::min(world_, 8));
 }
 
+void Engine::allreduce2(const double* src, double* dst, int64_t count) {
+  if (count <= 0) return;
+  if (world_ == 1) {
+    check(cudaMemcpyAsync(dst, src, sizeof(double) * count, cudaMemcpyDeviceToDevice, stream_), "D2D");
+    return;
+  }
+  ++collectives_;
+  if (nccl_comm_) {
+    const int rc = nccl().allreduce(src, dst, (size_t)count, kNcclDouble, kNcclSum, nccl_comm_, stream_);
+    if (rc != 0) throw Error{4, "ncclAllReduce failed"};
+    return;
+  }
+  std::vector<double> h((size_t)count);
+  check(cudaMemcpyAsync(h.data(), src, sizeof(double) * count, cudaMemcpyDeviceToHost, stream_), "D2H allreduce");
+  sync();
+  if (host_ar_(h.data(), count, host_ar_ctx_) != 0) throw Error{4, "host all-reduce callback failed"};
+  check(cudaMemcpyAsync(dst, h.data(), sizeof(double) * count, cudaMemcpyHostToDevice, stream_), "H2D allreduce");
+  sync();
+}
+
 void Engine::allreduce(double* dev, int64_t count) {
   if (world_ == 1 || count <= 0) return;
+  ++collectives_;
   if (nccl_comm_) {
     const int rc = nccl().allreduce(dev, dev, (size_t)count, kNcclDouble, kNcclSum, nccl_comm_, stream_);
     if (rc != 0) throw Error{4, "ncclAllReduce failed"};
@@ -445,6 +477,8 @@ void Engine::upload_rows_f32(View& v, const double* const* X, const int64_t* Nj,
 void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int D, const int64_t* ld, int layout) {
   if (J < 1 || D < 1 || X == nullptr || Nj == nullptr) throw_invalid("set_data: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_live_ = false;
+  host_stale_ = false;
   int64_t N = 0;
   for (int j = 0; j < J; ++j) {
     if (Nj[j] < 0 || (Nj[j] > 0 && X[j] == nullptr)) throw_invalid("set_data: bad group");
@@ -535,6 +569,8 @@ void Engine::set_data_host(int J, const double* const* X, const int64_t* Nj, int
 void Engine::set_data_device_f32(const float* X, int64_t N, int D, int64_t ld, const int32_t* gid, int J) {
   if (N < 0 || D < 1 || ld < D || J < 1 || (J > 1 && gid == nullptr)) throw_invalid("set_data_device: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_live_ = false;
+  host_stale_ = false;
   free_view(main_);
   // column sums on the device, then the mean over all ranks
   reserve(d_tmp_, sizeof(double) * (D + 1));
@@ -697,7 +733,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   if (full) {
     // statistics over the non-zero responsibilities only: per-cluster (row, q) lists, then a gathered scatter
     const bool reuse = list_valid_ && list_q_ == v.q && list_K_ == K && list_N_ == v.N && prec_ == kF32 && J == 1 &&
-                       !sparse_ && use_tc_ && dev::tc_supported(D, v.ldx);
+                       !sparse_ && use_tc_ && dev::tc_supported(D, v.ldx) && K <= dev::kTcCoarseMaxK;
     list_valid_ = false;
     if (v.N > 0 && reuse) {
       // the candidate lists of the last E pass cover every non-zero of q: gather their q (and N_k) instead of
@@ -747,7 +783,7 @@ void Engine::sphase(View& v, std::vector<WeightPost>& weights, std::vector<Clust
         void* lq = (unsigned char*)d_list_.p + rows_bytes;
         if (prec_ == kF32) {
           check(dev::nz_fill<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (float*)lq), "nz_fill");
-          if (use_tc_ && dev::tc_supported(D, v.ldx)) {
+          if (use_tc_ && dev::tc_supported(D, v.ldx) && K <= dev::kTcCoarseMaxK) {
             // power-of-two operand scale: scale * max|x - c| <= 2^14 for every row of the data set
             double cmax = 0;
             for (int k = 0; k < K; ++k)
@@ -861,7 +897,8 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
   const void* dMl = base + oL * es;
   const void* dC = base + oC * es;
   const void* dW = base + oW * es;
-  const uint8_t* d_act = (sparse_ && !act_.empty() && mode != dev::kERawLogit) ? (const uint8_t*)d_act_.p : nullptr;
+  // the mask belongs to the E step proper: the split ranking (cluster.cpp:401-415) and operator calls see every cluster
+  const uint8_t* d_act = (sparse_ && !act_.empty() && mode == dev::kEWrite) ? (const uint8_t*)d_act_.p : nullptr;
 
   reserve(d_small_, sizeof(double) * (K + 2));
   double* d_fz = (double*)d_small_.p;
@@ -1270,17 +1307,35 @@ double Engine::vbem(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   hints.resize(K);
   double F = DBL_MAX, Fold;
   int i = 0, n = 0;
-  do {
-    Fold = F;
-    iteration(v, weights, clusters, hints, &F);
-    ++n;
-    if (record) {
-      trace_F_.push_back(F);
-      trace_K_.push_back(K);
-    }
-    if ((F - Fold) / std::fabs(Fold) > kFengyDel) throw_runtime("Free energy increase!");
-    if (verbose_) std::cout << '-' << std::flush;
-  } while ((std::fabs((Fold - F) / Fold) > kConverge) && ((i++ < maxit) || (maxit < 0)));
+  // The iterations run against the device-resident model (statistics, posteriors and E-step operands never leave
+  // the GPU; the host reads one small record per iteration); the host objects are refreshed once at the end.
+  const bool on_device = use_dev_mstep_ && v.N > 0;
+  if (on_device) {
+    dev_drop();
+    dev_begin(v, weights, clusters, hints);
+  }
+  try {
+    do {
+      Fold = F;
+      if (on_device) dev_iteration(v, weights, &F);
+      else iteration(v, weights, clusters, hints, &F);
+      ++n;
+      if (record) {
+        trace_F_.push_back(F);
+        trace_K_.push_back(K);
+      }
+      if ((F - Fold) / std::fabs(Fold) > kFengyDel) throw_runtime("Free energy increase!");
+      if (verbose_) std::cout << '-' << std::flush;
+    } while ((std::fabs((Fold - F) / Fold) > kConverge) && ((i++ < maxit) || (maxit < 0)));
+  } catch (...) {
+    dev_live_ = false;
+    host_stale_ = false;
+    throw;
+  }
+  if (on_device) {
+    dev_sync_host(v, weights, clusters);
+    dev_live_ = false;
+  }
   if (iters) *iters = n;
   return F;
 }
@@ -1488,6 +1543,8 @@ bool Engine::split_gr(View& v, std::vector<WeightPost>& weights, std::vector<Clu
 // ------------------------------------------------------------ public fits ---
 void Engine::model_init(int model, double prior, double wprior, bool sparse) {
   if (main_.X == nullptr) throw_invalid("no observations loaded (call lcb_set_data first)");
+  dev_live_ = false;
+  host_stale_ = false;
   model_kinds(model, &wkind_, &ckind_);
   if (!(prior > 0)) throw_invalid("clustwidth must be > 0!");
   model_ = model;
@@ -1508,6 +1565,13 @@ void Engine::learn(int model, double prior, double wprior, int maxclusters, bool
                    unsigned nthreads, double* F, int* K) {
   if (nthreads < 1) throw_invalid("Must specify at least one thread for execution!");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  // nthreads bounds the host-side part of the fit, as omp_set_num_threads(nthreads) does in cluster.cpp:578
+  struct ThreadsGuard {
+    int& ref;
+    int saved;
+    ~ThreadsGuard() { ref = saved; }
+  } tguard{host_threads_, host_threads_};
+  host_threads_ = (int)std::max(1u, std::min((unsigned)host_threads_, nthreads));
   model_init(model, prior, wprior, sparse);
   verbose_ = verbose;
   list_valid_ = false;
@@ -1540,6 +1604,8 @@ void Engine::set_qz(const double* q0, int K) {
   if (model_ < 0) throw_invalid("call lcb_model_init first");
   if (K < 1 || q0 == nullptr) throw_invalid("set_qz: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_live_ = false;
+  host_stale_ = false;
   main_.K = 0;
   list_valid_ = false;
   ensure_q(main_, K);
@@ -1565,6 +1631,8 @@ void Engine::set_labels_device(const int32_t* labels, int K) {
   if (model_ < 0) throw_invalid("call lcb_model_init first");
   if (K < 1 || labels == nullptr) throw_invalid("set_labels: bad arguments");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_live_ = false;
+  host_stale_ = false;
   main_.K = 0;
   list_valid_ = false;
   ensure_q(main_, K);
@@ -1579,6 +1647,7 @@ void Engine::set_labels_device(const int32_t* labels, int K) {
 void Engine::vbem_public(int maxit, double* F, int* iters) {
   if (model_ < 0 || main_.K < 1) throw_invalid("model and responsibilities must be set first");
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_drop();
   trace_F_.clear();
   trace_K_.clear();
   v_ntot_ = N_total_;
@@ -1595,14 +1664,28 @@ void Engine::vbem_step(double* F) {
   while ((int)clusters_.size() < K) clusters_.emplace_back(ckind_, prior_, main_.D);
   hints_.resize(K);
   v_ntot_ = N_total_;
+  const bool on_device = use_dev_mstep_ && main_.N > 0;
+  if (on_device && !(dev_live_ && dev_view_ == &main_ && dev_K_ == K)) {
+    dev_drop();
+    dev_begin(main_, weights_, clusters_, hints_);
+  }
   const long l0 = launches_;
+  const int c0 = collectives_, s0 = syncs_;
   cudaEvent_t a, b;
   check(cudaEventCreate(&a), "event");
   check(cudaEventCreate(&b), "event");
   check(cudaEventRecord(a, stream_), "event");
   double f;
-  iteration(main_, weights_, clusters_, hints_, &f);
+  if (on_device) {
+    dev_iteration(main_, weights_, &f);
+    dev_live_ = true;
+    host_stale_ = true;
+  } else {
+    iteration(main_, weights_, clusters_, hints_, &f);
+  }
   check(cudaEventRecord(b, stream_), "event");
+  step_collectives_ = collectives_ - c0;
+  step_syncs_ = syncs_ - s0;
   sync();
   float ms = 0;
   cudaEventElapsedTime(&ms, ev_[0], ev_[1]);
@@ -1620,6 +1703,13 @@ void Engine::vbem_step(double* F) {
 
 void Engine::get_estep_detail(double out[8]) const {
   for (int i = 0; i < 8; ++i) out[i] = estep_detail_[i];
+}
+
+void Engine::get_step_counts(double out[4]) {
+  out[0] = (double)step_launches_;
+  out[1] = (double)step_collectives_;
+  out[2] = (double)step_syncs_;
+  out[3] = use_dev_mstep_ ? 1.0 : 0.0;
 }
 
 void Engine::get_step_timing(double out[4]) {
@@ -1660,6 +1750,7 @@ void Engine::get_qz(int j, double* out, int64_t ld, int layout) {
 }
 
 void Engine::get_group_weights(int j, double* Nk, double* Elogw, double* fen) {
+  ensure_host_model();
   if (j < 0 || j >= (int)weights_.size()) throw_invalid("get_group_weights: bad group");
   const WeightPost& w = weights_[j];
   if (Nk) std::copy(w.getNk().begin(), w.getNk().end(), Nk);
@@ -1669,6 +1760,7 @@ void Engine::get_group_weights(int j, double* Nk, double* Elogw, double* fen) {
 
 void Engine::get_cluster(int k, double* N_s, double* x_s, double* xx_s, double* N, double* mean, double* cov,
                          double* fen) {
+  ensure_host_model();
   if (k < 0 || k >= (int)clusters_.size()) throw_invalid("get_cluster: bad cluster");
   const ClusterPost& c = clusters_[k];
   if (N_s) *N_s = c.N_s();
@@ -1703,6 +1795,7 @@ void Engine::op_addobs(ClusterPost& c, const double* qk, const double* X, int64_
   if (N < 0 || (N > 0 && (X == nullptr || qk == nullptr))) throw_invalid("addobs: bad arguments");
   if (N == 0) return;
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_drop();
   // temporary view with its own centring; engine state is saved and restored
   View saved = main_;
   std::vector<double> saved_centre = centre_;
@@ -1763,6 +1856,7 @@ void Engine::op_eloglike(const ClusterPost& c, const double* X, int64_t N, int64
   if (N < 0 || (N > 0 && (X == nullptr || out == nullptr))) throw_invalid("Eloglike: bad arguments");
   if (N == 0) return;
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_drop();
   View saved = main_;
   std::vector<double> saved_centre = centre_;
   const int saved_ck = ckind_;
@@ -1813,6 +1907,7 @@ void Engine::op_splitobs(const ClusterPost& c, const double* X, int64_t N, int64
   if (N < 0 || (N > 0 && (X == nullptr || out == nullptr))) throw_invalid("splitobs: bad arguments");
   if (N == 0) return;
   check(cudaSetDevice(device_), "cudaSetDevice");
+  dev_drop();
   View tmp;
   void* d_flags = nullptr;
   try {

@@ -64,6 +64,7 @@ class Engine {
   const std::vector<double>& trace_F() const { return trace_F_; }
   const std::vector<int>& trace_K() const { return trace_K_; }
   void get_step_timing(double out[4]);
+  void get_step_counts(double out[4]);  // launches, collectives, host synchronisations of the last vbem_step
   void get_estep_detail(double out[8]) const;
   cudaStream_t stream() const { return stream_; }
 
@@ -105,6 +106,30 @@ class Engine {
                 std::vector<int>& tally, double F, int maxclusters);
   void build_act(const std::vector<double>& Njk, int J, int K);
   void allreduce(double* dev, int64_t count);
+  void allreduce2(const double* src, double* dst, int64_t count);  // out of place (device pointers)
+
+  // ---- device-resident M step (engine_dev.cu, mstep.cu): the default path of vbem() and vbem_step() ----
+  struct TcLayout {
+    size_t off_f, off_aug, off_cpar, total, naug;
+  };
+  TcLayout tc_layout(int J, int K, bool two) const;
+  void dev_begin(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters,
+                 std::vector<std::vector<double>>& hints);
+  void dev_iteration(View& v, const std::vector<WeightPost>& weights, double* F);
+  void dev_sphase(View& v);
+  void dev_two_level(View& v, int K, const TcLayout& lay, bool first_try);
+  void dev_sync_host(View& v, std::vector<WeightPost>& weights, std::vector<ClusterPost>& clusters);
+  void dev_drop();          // host objects up to date, device model forgotten
+  void ensure_host_model(); // getters: refresh the host objects from the device statistics if they are stale
+  bool use_dev_mstep_ = true;   // LCB_HOST_MSTEP=1 keeps the posterior updates on the host (A/B checks)
+  bool dev_live_ = false;       // the device holds the posterior of (dev_view_, dev_K_): its centres feed the next pass
+  bool host_stale_ = false;     // weights_/clusters_ lag the device model
+  const View* dev_view_ = nullptr;
+  int dev_K_ = 0;
+  long long elist_cap_ = 0, slist_cap_ = 0;   // capacity (entries) of the candidate lists / the non-zero lists
+  double last_pairs_ = 0, last_nnz_s_ = 0;
+  double* h_iter_ = nullptr;    // page-locked copy of the iteration record
+  DeviceBuf d_raw_, d_post_, d_work_, d_iter_, d_centre_, d_wscr_, d_vaug_;
   void allreduce_host(double* host, int64_t count);
   void share_host_threads();
   void check(cudaError_t e, const char* what) const;
@@ -160,6 +185,7 @@ class Engine {
   cudaEvent_t ev_[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   double t_s_ = 0, t_e_ = 0, t_all_ = 0;
   long launches_ = 0, step_launches_ = 0;
+  int collectives_ = 0, step_collectives_ = 0, syncs_ = 0, step_syncs_ = 0;
 
   // communication
   int rank_ = 0, world_ = 1;

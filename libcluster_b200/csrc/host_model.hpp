@@ -46,6 +46,9 @@ class WeightPost {
   const std::vector<double>& Elogweight() const { return Elogpi_; }
   const std::vector<double>& getNk() const { return Nk_; }
   int kind() const { return kind_; }
+  double prior1() const { return a1p_; }
+  double prior2() const { return a2p_; }
+  double prior_fenergy() const { return Fp_; }
 
  private:
   int kind_;
@@ -91,6 +94,7 @@ class ClusterPost {
   double nu() const { return nu_; }
   double beta() const { return beta_; }
   double logdW() const { return logdW_; }
+  double prior_fenergy() const { return F_p_; }
 
   // E[log p(x)] = cconst - 0.5 * || R (x - m) ||^2   with R lower-triangular
   // (GaussWish: sqrt(nu) L^-1, iW = L L^T) or diagonal (NormGamma:

@@ -124,8 +124,10 @@ __global__ void __launch_bounds__(kThreads)
 estep_full_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ gid, int K,
                   const T* __restrict__ RT, const T* __restrict__ mhi, const T* __restrict__ mlo,
                   const T* __restrict__ chat, const T* __restrict__ lw, const uint8_t* __restrict__ act,
-                  T* __restrict__ q, int64_t ldq, int mode, double* __restrict__ Fz, double* __restrict__ H) {
+                  T* __restrict__ q, int64_t ldq, int mode, double* __restrict__ Fz, double* __restrict__ H,
+                  const unsigned* __restrict__ skip) {
   constexpr int DP = 16 * TN, TM = 16 * PT, XS = TM + 4, DC = 8;
+  if (skip != nullptr && *skip != 0u) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* XT = reinterpret_cast<T*>(smem_raw);  // [DP][XS] tile, dimension-major
   T* XcT = XT + DP * XS;                   // [DP][XS] centred on the current cluster
@@ -227,8 +229,10 @@ __global__ void __launch_bounds__(kThreads)
 estep_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const int32_t* __restrict__ gid, int K,
                   const T* __restrict__ A, const T* __restrict__ mhi, const T* __restrict__ mlo,
                   const T* __restrict__ chat, const T* __restrict__ lw, const uint8_t* __restrict__ act,
-                  T* __restrict__ q, int64_t ldq, int mode, double* __restrict__ Fz, double* __restrict__ H) {
+                  T* __restrict__ q, int64_t ldq, int mode, double* __restrict__ Fz, double* __restrict__ H,
+                  const unsigned* __restrict__ skip) {
   constexpr int TM = 64, KT = 64, DC = 32, XS = TM + 4, KS = KT + 4;
+  if (skip != nullptr && *skip != 0u) return;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* Xch = reinterpret_cast<T*>(smem_raw);  // [DC][XS]
   T* Ach = Xch + DC * XS;                   // [DC][KS]
@@ -494,8 +498,10 @@ template <typename T>
 __global__ void __launch_bounds__(kThreads)
 nz_fill_kernel(const T* __restrict__ q, int64_t ldq, int64_t N, int K, const int32_t* __restrict__ gid,
                const uint8_t* __restrict__ act, int kw, const int32_t* __restrict__ blockoff,
-               const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq, int pred) {
+               const long long* __restrict__ koff, int32_t* __restrict__ lrow, T* __restrict__ lq, int pred,
+               const unsigned* __restrict__ skip) {
   extern __shared__ int scnt[];
+  if (skip != nullptr && *skip != 0u) return;
   for (int k = threadIdx.x; k < K; k += kThreads) scnt[k] = 0;
   __syncthreads();
   const int kl = threadIdx.x % kw, rl = threadIdx.x / kw, rw = kThreads / kw;
@@ -532,7 +538,8 @@ __global__ void __launch_bounds__(kThreads)
 sstat_gather_full_kernel(const T* __restrict__ X, int D, int64_t ldx, const int32_t* __restrict__ lrow,
                          const T* __restrict__ lq, const long long* __restrict__ koff,
                          const long long* __restrict__ kcnt, int DPc, const T* __restrict__ cen, int nb,
-                         double* __restrict__ xs, double* __restrict__ S) {
+                         double* __restrict__ xs, double* __restrict__ S, const unsigned* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0u) return;
   constexpr int BW = 16 * TN, TMS = sizeof(T) == 8 ? 16 : 32;
   constexpr bool kStage = sizeof(T) == 4;  // fp32: fold into fp64 shared accumulators every 2 sub-tiles
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -548,11 +555,11 @@ sstat_gather_full_kernel(const T* __restrict__ X, int D, int64_t ldx, const int3
   const int bi = blockIdx.z / nb, bj = blockIdx.z - bi * nb;
   const int i0 = bi * BW, j0 = bj * BW;
   const long long cnt = kcnt[k];
-  const long long l0 = (long long)blockIdx.x * kGatherChunk;
-  if (l0 >= cnt) return;
-  const long long l1 = (l0 + kGatherChunk < cnt) ? l0 + kGatherChunk : cnt;
   const long long base = koff[k];
   const T* ck = cen + (size_t)k * DPc;
+  // the grid's x extent is sized from a bound on the longest list; chunks beyond it are walked by striding
+  for (long long l0 = (long long)blockIdx.x * kGatherChunk; l0 < cnt; l0 += (long long)gridDim.x * kGatherChunk) {
+  const long long l1 = (l0 + kGatherChunk < cnt) ? l0 + kGatherChunk : cnt;
 
   T acc[TN][TN];
 #pragma unroll
@@ -629,6 +636,8 @@ sstat_gather_full_kernel(const T* __restrict__ X, int D, int64_t ldx, const int3
     double v = (double)xacc;
     if (kStage) v += xsacc[tid];
     if (v != 0.0) atomicAdd(&xs[(size_t)k * D + i0 + tid], v);
+  }
+  __syncthreads();
   }
 }
 
@@ -1026,7 +1035,7 @@ template <typename T, int TN, int PT>
 static cudaError_t launch_estep_full(cudaStream_t st, int sms, long smem, const T* X, int64_t N, int D, int64_t ldx,
                                      const int32_t* gid, int K, const T* RT, const T* mhi, const T* mlo, const T* chat,
                                      const T* lw, const uint8_t* act, T* q, int64_t ldq, int mode, double* Fz,
-                                     double* H) {
+                                     double* H, const unsigned* skip) {
   auto kern = estep_full_kernel<T, TN, PT>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -1037,14 +1046,14 @@ static cudaError_t launch_estep_full(cudaStream_t st, int sms, long smem, const 
   int64_t grid = (int64_t)sms * occ;
   if (grid > ntiles) grid = ntiles;
   if (grid < 1) grid = 1;
-  kern<<<(int)grid, kThreads, smem, st>>>(X, N, D, ldx, gid, K, RT, mhi, mlo, chat, lw, act, q, ldq, mode, Fz, H);
+  kern<<<(int)grid, kThreads, smem, st>>>(X, N, D, ldx, gid, K, RT, mhi, mlo, chat, lw, act, q, ldq, mode, Fz, H, skip);
   return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t estep_full(cudaStream_t st, int sms, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid, int K,
                        const T* RT, const T* mhi, const T* mlo, const T* chat, const T* lw, const uint8_t* act, T* q,
-                       int64_t ldq, int mode, double* Fz, double* H) {
+                       int64_t ldq, int mode, double* Fz, double* H, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   const int DP = full_dp(D);
   const long smem = estep_full_smem<T>(D, K);
@@ -1053,9 +1062,9 @@ cudaError_t estep_full(cudaStream_t st, int sms, const T* X, int64_t N, int D, i
 #define LCB_CASE(TNV)                                                                                              \
   case 16 * TNV:                                                                                                   \
     return PT == 4 ? launch_estep_full<T, TNV, 4>(st, sms, smem, X, N, D, ldx, gid, K, RT, mhi, mlo, chat, lw, act, \
-                                                  q, ldq, mode, Fz, H)                                             \
+                                                  q, ldq, mode, Fz, H, skip)                                       \
                    : launch_estep_full<T, TNV, 2>(st, sms, smem, X, N, D, ldx, gid, K, RT, mhi, mlo, chat, lw, act, \
-                                                  q, ldq, mode, Fz, H);
+                                                  q, ldq, mode, Fz, H, skip);
   switch (DP) {
     LCB_CASE(1)
     LCB_CASE(2)
@@ -1070,7 +1079,7 @@ cudaError_t estep_full(cudaStream_t st, int sms, const T* X, int64_t N, int D, i
 template <typename T>
 cudaError_t estep_diag(cudaStream_t st, int sms, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid, int K,
                        const T* A, const T* mhi, const T* mlo, const T* chat, const T* lw, const uint8_t* act, T* q,
-                       int64_t ldq, int mode, double* Fz, double* H) {
+                       int64_t ldq, int mode, double* Fz, double* H, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   const long smem = estep_diag_smem<T>(D, K);
   if (smem < 0 || K > 512) return cudaErrorInvalidValue;
@@ -1083,7 +1092,7 @@ cudaError_t estep_diag(cudaStream_t st, int sms, const T* X, int64_t N, int D, i
   if (occ < 1) occ = 1;
   int64_t grid = (int64_t)sms * occ;
   if (grid > ntiles) grid = ntiles;
-  kern<<<(int)grid, kThreads, smem, st>>>(X, N, D, ldx, gid, K, A, mhi, mlo, chat, lw, act, q, ldq, mode, Fz, H);
+  kern<<<(int)grid, kThreads, smem, st>>>(X, N, D, ldx, gid, K, A, mhi, mlo, chat, lw, act, q, ldq, mode, Fz, H, skip);
   return cudaGetLastError();
 }
 
@@ -1128,12 +1137,12 @@ cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, 
 }
 template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred) {
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   int kw = 1;
   while (kw < K && kw < kThreads) kw <<= 1;
   nz_fill_kernel<T><<<(unsigned)nz_blocks(N), kThreads, sizeof(int) * K, st>>>(q, ldq, N, K, gid, act, kw, blockoff, koff,
-                                                                            lrow, lq, pred);
+                                                                            lrow, lq, pred, skip);
   return cudaGetLastError();
 }
 int64_t nz_blocks(int64_t N) { return (N + kNzBlock - 1) / kNzBlock; }
@@ -1141,34 +1150,35 @@ int64_t nz_blocks(int64_t N) { return (N + kNzBlock - 1) / kNzBlock; }
 template <typename T, int TN>
 static cudaError_t launch_gather_full(cudaStream_t st, dim3 grid, const T* X, int D, int64_t ldx, const int32_t* lrow,
                                       const T* lq, const long long* koff, const long long* kcnt, int DP, const T* cen,
-                                      int nb, double* xs, double* S) {
+                                      int nb, double* xs, double* S, const unsigned* skip) {
   constexpr int BW = 16 * TN, TMS = sizeof(T) == 8 ? 16 : 32;
   size_t smem = (((size_t)(2 * TMS * BW + TMS) * sizeof(T) + TMS * 4 + 15) & ~(size_t)15);
   if (sizeof(T) == 4) smem += sizeof(double) * ((size_t)TN * TN * kThreads + BW);
   auto kern = sstat_gather_full_kernel<T, TN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, kThreads, smem, st>>>(X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+  kern<<<grid, kThreads, smem, st>>>(X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S, skip);
   return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
                               const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
-                              double* xs, double* S) {
+                              double* xs, double* S, const unsigned* skip) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
   const int DP = full_dp(D);
   if (DP == 0) return cudaErrorInvalidValue;
   const int tn = DP >= 128 ? 8 : DP / 16;
   const int nb = (D + 16 * tn - 1) / (16 * tn);
-  const long long chunks = (maxcnt + kGatherChunk - 1) / kGatherChunk;
-  if (chunks > 2147483647LL || K > 65535) return cudaErrorInvalidValue;
+  long long chunks = (maxcnt + kGatherChunk - 1) / kGatherChunk;
+  if (chunks > 4096) chunks = 4096;  // longer lists are strided over
+  if (K > 65535) return cudaErrorInvalidValue;
   dim3 grid((unsigned)chunks, K, nb * nb);
   switch (tn) {
-    case 1: return launch_gather_full<T, 1>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
-    case 2: return launch_gather_full<T, 2>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
-    case 4: return launch_gather_full<T, 4>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
-    default: return launch_gather_full<T, 8>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S);
+    case 1: return launch_gather_full<T, 1>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S, skip);
+    case 2: return launch_gather_full<T, 2>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S, skip);
+    case 4: return launch_gather_full<T, 4>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S, skip);
+    default: return launch_gather_full<T, 8>(st, grid, X, D, ldx, lrow, lq, koff, kcnt, DP, cen, nb, xs, S, skip);
   }
 }
 
@@ -1301,10 +1311,10 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
   template long estep_diag_smem<T>(int, int);                                                                         \
   template cudaError_t estep_full<T>(cudaStream_t, int, const T*, int64_t, int, int64_t, const int32_t*, int,         \
                                      const T*, const T*, const T*, const T*, const T*, const uint8_t*, T*, int64_t,  \
-                                     int, double*, double*);                                                          \
+                                     int, double*, double*, const unsigned*);                                         \
   template cudaError_t estep_diag<T>(cudaStream_t, int, const T*, int64_t, int, int64_t, const int32_t*, int,         \
                                      const T*, const T*, const T*, const T*, const T*, const uint8_t*, T*, int64_t,  \
-                                     int, double*, double*);                                                          \
+                                     int, double*, double*, const unsigned*);                                         \
   template cudaError_t sstat_full<T>(cudaStream_t, const T*, int64_t, int, int64_t, const int32_t*, const T*,         \
                                      int64_t, int, const T*, const uint8_t*, double*, double*);                       \
   template cudaError_t sstat_diag<T>(cudaStream_t, const T*, int64_t, int, int64_t, const int32_t*, const T*,         \
@@ -1313,10 +1323,10 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
   template cudaError_t nz_count<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,     \
                                    int32_t*, double*, int);                                                           \
   template cudaError_t nz_fill<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,      \
-                                  const int32_t*, const long long*, int32_t*, T*, int);                               \
+                                  const int32_t*, const long long*, int32_t*, T*, int, const unsigned*);              \
   template cudaError_t sstat_gather_full<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \
                                             const long long*, const long long*, long long, int, const T*, double*,   \
-                                            double*);                                                                 \
+                                            double*, const unsigned*);                                                \
   template cudaError_t convert_rows<T>(cudaStream_t, const double*, int64_t, int, int64_t, int, const double*, T*,    \
                                        int64_t);                                                                      \
   template cudaError_t convert_f32<T>(cudaStream_t, const float*, int64_t, int, int64_t, const double*, T*, int64_t); \

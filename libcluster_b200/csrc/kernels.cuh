@@ -32,12 +32,16 @@ template <typename T> long estep_diag_smem(int D, int K);
 template <typename T>
 cudaError_t estep_full(cudaStream_t st, int sms, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid,
                        int K, const T* RT, const T* mhi, const T* mlo, const T* chat, const T* lw,
-                       const uint8_t* act, T* q, int64_t ldq, int mode, double* Fz, double* H);
+                       const uint8_t* act, T* q, int64_t ldq, int mode, double* Fz, double* H,
+                       const unsigned* skip = nullptr);
 
 template <typename T>
 cudaError_t estep_diag(cudaStream_t st, int sms, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid,
                        int K, const T* A, const T* mhi, const T* mlo, const T* chat, const T* lw,
-                       const uint8_t* act, T* q, int64_t ldq, int mode, double* Fz, double* H);
+                       const uint8_t* act, T* q, int64_t ldq, int mode, double* Fz, double* H,
+                       const unsigned* skip = nullptr);
+// `skip` (device word, may be NULL): the kernel returns at once when it is non-zero -- the iteration was aborted on
+// the device (list overflow, failed M step) and the host repeats or reports it (mstep.cuh).
 
 // Sufficient statistics about per-cluster centres cen [K][DP] (full) / [K][D] (diag).
 template <typename T>
@@ -62,11 +66,12 @@ cudaError_t nz_count(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K,
 cudaError_t nz_scan(cudaStream_t st, int32_t* blockcnt, int64_t nblocks, int K, long long* total /* [K] */);
 template <typename T>
 cudaError_t nz_fill(cudaStream_t st, const T* q, int64_t ldq, int64_t N, int K, const int32_t* gid, const uint8_t* act,
-                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred = kNzNonZero);
+                    const int32_t* blockoff, const long long* koff, int32_t* lrow, T* lq, int pred = kNzNonZero,
+                    const unsigned* skip = nullptr);
 template <typename T>
 cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
                               const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
-                              double* xs, double* S);
+                              double* xs, double* S, const unsigned* skip = nullptr);
 
 // ---- data movement / labels / split bookkeeping ---------------------------
 // dst[n][d] = T(src[n][d] - mean[d]) from a staged block of doubles in either order

@@ -257,8 +257,10 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
                    const float* __restrict__ inv_t2, const float* __restrict__ chat, const float* __restrict__ lw,
                    const uint8_t* __restrict__ act, float* __restrict__ q, int64_t ldq, double* __restrict__ Fz,
                    unsigned* __restrict__ err, const int32_t* __restrict__ lrow, const int4* __restrict__ items,
-                   int64_t nitems) {
+                   int64_t nitems, const long long* __restrict__ nitems_dev, const unsigned* __restrict__ skip) {
   extern __shared__ unsigned char smem_dyn[];
+  if (skip != nullptr && *skip != 0u) return;
+  if (kList && nitems_dev != nullptr) nitems = (int64_t)*nitems_dev;  // planned on the device (list_plan)
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
   const uint32_t sB = sbase, sBar = sbase + kOffBar;
@@ -655,8 +657,11 @@ __global__ void __launch_bounds__(kScatterThreads, 1)
 sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow, const float* __restrict__ lq,
                    const long long* __restrict__ koff, const long long* __restrict__ kcnt, int K,
                    const float* __restrict__ cen, float scale, int chunk_rows, double* __restrict__ xs,
-                   double* __restrict__ S, unsigned* __restrict__ err) {
+                   double* __restrict__ S, unsigned* __restrict__ err, const float* __restrict__ scale_dev,
+                   const unsigned* __restrict__ skip) {
   extern __shared__ unsigned char smem_dyn[];
+  if (skip != nullptr && *skip != 0u) return;
+  if (scale_dev != nullptr) scale = *scale_dev;  // chosen by the device M step from the centres it produced
   const uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
   unsigned char* sgen = smem_dyn + (sbase - smem_u32(smem_dyn));
   const uint32_t sBar = sbase + kSOffBar;
@@ -1107,8 +1112,13 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
                           const uint8_t* __restrict__ augblob, const float* __restrict__ cpar /* [4][K] */,
                           const float* __restrict__ lw, const uint8_t* __restrict__ act, float sg, uint32_t aug01,
                           uint32_t aug2, float margin, float* __restrict__ q, int64_t ldq,
-                          uint32_t* __restrict__ cmask, uint32_t sbase_hint, unsigned* __restrict__ err) {
+                          uint32_t* __restrict__ cmask, uint32_t sbase_hint, unsigned* __restrict__ err,
+                          const unsigned* __restrict__ augh_dev, const unsigned* __restrict__ skip) {
   extern __shared__ unsigned char smem_dyn[];
+  if (augh_dev != nullptr) {  // 2^P of the centring chunk chosen by the device M step (both fp16 halves)
+    aug01 = *augh_dev;
+    aug2 = aug01 & 0xffffu;
+  }
   // opaque copies: the compiler would otherwise rematerialise these from special registers (S2R / S2UR, ~50 cycles
   // each) inside the per-item loops, where registers are tight
   uint32_t sbase = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -1129,6 +1139,7 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     if (tid == 0 && blockIdx.x == 0) err[1] = 0x80000000u | sbase;
     return;
   }
+  if (skip != nullptr && (skip[0] | skip[1]) != 0u) return;  // aborted iteration, or the dense kernel runs instead
   const int warp = (int)(tid >> 5), lane = (int)(tid & 31);
   const int64_t ngroups = (N + kCRows - 1) / kCRows;
 
@@ -1425,8 +1436,9 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
 template <int LGP>  // log2 of the lanes that share a row in phase B: 4 << LGP >= K
 __global__ void __launch_bounds__(256)
 estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, const uint32_t* __restrict__ cmask, int W,
-                      double* __restrict__ Fz) {
+                      double* __restrict__ Fz, const unsigned* __restrict__ skip) {
   constexpr int GP = 1 << LGP, WMAX = (4 * GP + 31) / 32;
+  if (skip != nullptr && (skip[0] | skip[1]) != 0u) return;
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1522,8 +1534,9 @@ constexpr int kMaskBlock = 2048;  // == kNzBlock
 template <bool kFill>
 __global__ void __launch_bounds__(256)
 mask_lists_kernel(const uint32_t* __restrict__ cmask, int W, int64_t N, int K, int32_t* __restrict__ blockcnt,
-                  const long long* __restrict__ koff, int32_t* __restrict__ lrow) {
+                  const long long* __restrict__ koff, int32_t* __restrict__ lrow, const unsigned* __restrict__ skip) {
   extern __shared__ int scnt[];
+  if (skip != nullptr && (skip[0] | skip[1]) != 0u) return;
   for (int k = threadIdx.x; k < K; k += 256) scnt[k] = 0;
   __syncthreads();
   const int64_t r0 = (int64_t)blockIdx.x * kMaskBlock;
@@ -1550,11 +1563,18 @@ mask_lists_kernel(const uint32_t* __restrict__ cmask, int W, int64_t N, int K, i
 // Work items of level 2: 128-entry chunks of the per-cluster lists, resolved once instead of by every warp role
 __global__ void __launch_bounds__(256)
 build_items_kernel(const int32_t* __restrict__ itoff, const long long* __restrict__ koff,
-                   const long long* __restrict__ kcnt, int K, int64_t nitems, int4* __restrict__ items) {
-  const int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= nitems) return;
-  const ListItem r = list_item(it, K, itoff, koff, kcnt);
-  items[it] = make_int4(r.k, r.count, (int)(r.base & 0xffffffffLL), (int)(r.base >> 32));
+                   const long long* __restrict__ kcnt, int K, int64_t nitems, int4* __restrict__ items,
+                   const long long* __restrict__ nitems_dev, const unsigned* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0u) return;
+  if (nitems_dev != nullptr) {
+    const int64_t cap = nitems;
+    nitems = (int64_t)*nitems_dev;
+    if (nitems > cap) nitems = cap;
+  }
+  for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < nitems; it += (int64_t)gridDim.x * blockDim.x) {
+    const ListItem r = list_item(it, K, itoff, koff, kcnt);
+    items[it] = make_int4(r.k, r.count, (int)(r.base & 0xffffffffLL), (int)(r.base >> 32));
+  }
 }
 
 // lq[e] = q[lrow[e]][k] for every entry of cluster k's list and Nk[k] = sum_e lq[e]: the statistics pass can then
@@ -1602,30 +1622,35 @@ bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
 
 cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
-                        const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err) {
+                        const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err,
+                        const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (N + kTM - 1) / kTM;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   estep_tc128_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q,
-                                                                  ldq, Fz, err, nullptr, nullptr, 0);
+                                                                  ldq, Fz, err, nullptr, nullptr, 0, nullptr, skip);
   return cudaGetLastError();
 }
 
 cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                              const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                              const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
-                             const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err) {
-  if (N <= 0 || nitems <= 0) return cudaSuccess;
-  build_items_kernel<<<(unsigned)((nitems + 255) / 256), 256, 0, st>>>(itoff, koff, kcnt, K, nitems, (int4*)items);
+                             const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err,
+                             const long long* nitems_dev, const unsigned* skip) {
+  if (N <= 0 || (nitems <= 0 && nitems_dev == nullptr)) return cudaSuccess;
+  // nitems_dev != NULL: the item count lives on the device; `nitems` is then the capacity of `items`
+  const int64_t bgrid = nitems_dev ? (int64_t)sms * 8 : (nitems + 255) / 256;
+  build_items_kernel<<<(unsigned)bgrid, 256, 0, st>>>(itoff, koff, kcnt, K, nitems, (int4*)items, nitems_dev, skip);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(estep_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
-  const int grid = (int)(nitems < sms ? nitems : sms);
+  const int grid = (int)(nitems < sms && nitems_dev == nullptr ? nitems : sms);
   estep_tc128_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, nullptr, q,
-                                                                 ldq, nullptr, err, lrow, (const int4*)items, nitems);
+                                                                 ldq, nullptr, err, lrow, (const int4*)items, nitems,
+                                                                 nitems_dev, skip);
   return cudaGetLastError();
 }
 
@@ -1633,7 +1658,7 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
                                float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
-                               unsigned* err) {
+                               unsigned* err, const unsigned* augh_dev, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
   cudaError_t e = cudaFuncSetAttribute(estep_coarse_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
@@ -1642,20 +1667,21 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
   const int grid = (int)(ngroups < sms ? ngroups : sms);
   const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
   estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
-                                                                   h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, err);
+                                                                   h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, err,
+                                                                   augh_dev, skip);
   return cudaGetLastError();
 }
 
 cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
-                           double* Fz) {
+                           double* Fz, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   if (K > 256 || (ldq & 3)) return cudaErrorInvalidValue;
   const int W = (K + 31) / 32;
   const int grid = sms * 16;
-  if (K <= 32) estep_finalize_kernel<3><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else if (K <= 64) estep_finalize_kernel<4><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else if (K <= 128) estep_finalize_kernel<5><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
-  else estep_finalize_kernel<6><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz);
+  if (K <= 32) estep_finalize_kernel<3><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
+  else if (K <= 64) estep_finalize_kernel<4><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
+  else if (K <= 128) estep_finalize_kernel<5><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
+  else estep_finalize_kernel<6><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
   return cudaGetLastError();
 }
 
@@ -1666,18 +1692,18 @@ cudaError_t apply_candidate_mask(cudaStream_t st, float* q, int64_t ldq, int64_t
   return cudaGetLastError();
 }
 
-cudaError_t mask_count(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockcnt) {
+cudaError_t mask_count(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockcnt, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   mask_lists_kernel<false><<<(unsigned)((N + kMaskBlock - 1) / kMaskBlock), 256, sizeof(int) * K, st>>>(
-      cmask, (K + 31) / 32, N, K, blockcnt, nullptr, nullptr);
+      cmask, (K + 31) / 32, N, K, blockcnt, nullptr, nullptr, skip);
   return cudaGetLastError();
 }
 
 cudaError_t mask_fill(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, int32_t* blockoff, const long long* koff,
-                      int32_t* lrow) {
+                      int32_t* lrow, const unsigned* skip) {
   if (N <= 0) return cudaSuccess;
   mask_lists_kernel<true><<<(unsigned)((N + kMaskBlock - 1) / kMaskBlock), 256, sizeof(int) * K, st>>>(
-      cmask, (K + 31) / 32, N, K, blockoff, koff, lrow);
+      cmask, (K + 31) / 32, N, K, blockoff, koff, lrow, skip);
   return cudaGetLastError();
 }
 
@@ -1725,7 +1751,8 @@ double tc_pack_aug(const double* w /* [128] */, int k, uint8_t* augblob) {
 
 cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t* lrow, const float* lq,
                         const long long* koff, const long long* kcnt, long long maxcnt, long long nnz, int K,
-                        const float* cen, float scale, double* xs, double* S, unsigned* err) {
+                        const float* cen, float scale, double* xs, double* S, unsigned* err, const float* scale_dev,
+                        const unsigned* skip) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
   // rows folded into one fp32 TMEM accumulator before the fp64 add: fewer for small problems (more accurate, and the
   // extra atomics are free there), kTcScatterChunk for large ones
@@ -1737,7 +1764,7 @@ cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t*
   if (K > kTcCoarseMaxK || items_max > 2000000000LL) return cudaErrorInvalidValue;
   const int grid = (int)(items_max < sms ? items_max : sms);
   sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, K, cen, scale, chunk_rows, xs,
-                                                                 S, err);
+                                                                 S, err, scale_dev, skip);
   return cudaGetLastError();
 }
 

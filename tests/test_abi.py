@@ -135,3 +135,31 @@ def test_shard_rows_partition():
                 assert a[1] == b[0]
             sizes = [e - b for b, e in cuts]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 16, 17, 33, 64, 100, 256, 512])
+def test_device_stick_order_is_std_sort(n):
+    """The device M step orders sticks with a restatement of libstdc++'s std::sort (mstep_math.hpp): same order as
+    the reference's std::sort call (distributions.cpp:146) on random, tie-heavy and adversarial counts."""
+    import ctypes as C
+    L = nat.lib()
+    rng = np.random.default_rng(n)
+    cases = [rng.uniform(0, 50, n), np.zeros(n), np.arange(n, dtype=float), np.arange(n, dtype=float)[::-1].copy(),
+             rng.integers(0, 3, n).astype(float), np.where(rng.random(n) < 0.7, 0.0, rng.uniform(0, 9, n)),
+             np.tile([5.0, 1.0], n)[:n].copy(), np.r_[np.arange(n // 2), np.arange(n - n // 2)].astype(float)]
+    # median-of-three killer sequence (drives introsort into its heap-sort fallback for larger n)
+    if n >= 4 and n % 2 == 0:
+        k = n // 2
+        mk = np.zeros(n)
+        for i in range(1, k + 1):
+            mk[i - 1] = i if i % 2 == 1 else k + i - 1
+            mk[k + i - 1] = 2 * i
+        cases.append(-mk)
+    for v in cases:
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        order = np.zeros(n, dtype=np.int32)
+        diff = L.lcb_selftest_stick_order(v.ctypes.data_as(C.POINTER(C.c_double)), n,
+                                          order.ctypes.data_as(C.POINTER(C.c_int)))
+        assert diff == 0
+        assert sorted(order.tolist()) == list(range(n))
+        assert np.all(np.diff(v[order]) <= 0)
