@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 
 CHUNK = 250_000          # rows per generation chunk; shards are whole chunks
 SEED = 20260925
+SOFT_SPREADS = [1.0, 0.5]   # means U(-s, s)^D of the extra soft-regime points (see soft_point)
 # fallback only if MEASURED_PEAKS.json is absent (/opt/skills/guides/B200_PROFILING.md)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -47,6 +48,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--spread", type=float, default=10.0,
+                    help="cluster means ~ U(-spread, spread)^D (SURVEY 8d: 10); small values make clusters overlap")
+    ap.add_argument("--soft-spreads", default="auto",
+                    help="comma-separated spreads of the extra soft-regime points (N=1 only; 'none' to skip)")
+    ap.add_argument("--soft-rows", type=int, default=8_000_000, help="rows of each soft-regime point")
     return ap.parse_args()
 
 
@@ -65,10 +71,11 @@ def peaks():
 
 
 # ------------------------------------------------------------------ data ---
-def mixture_params(D, K, diag=False):
-    """means U(-10,10)^D, covariances A A^T / D + 0.5 I (or diag(U(0.5,2))), weights Dirichlet(5)."""
+def mixture_params(D, K, diag=False, spread=10.0):
+    """means U(-10,10)^D, covariances A A^T / D + 0.5 I (or diag(U(0.5,2))), weights Dirichlet(5).
+    `spread` replaces the 10: the same unit draws scaled, so the covariances and weights do not change with it."""
     rng = np.random.default_rng(SEED)
-    mu = rng.uniform(-10, 10, size=(K, D))
+    mu = rng.uniform(-10, 10, size=(K, D)) * (spread / 10.0)
     if diag:
         L = np.sqrt(rng.uniform(0.5, 2.0, size=(K, D)))     # per-dimension standard deviations
     else:
@@ -231,6 +238,47 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------- soft regime ---
+def soft_point(torch, lc, dev, D, K, rows, spread, steps=3, warmup=3):
+    """One extra measured point on a mixture whose clusters overlap (means U(-spread, spread)^D): the two-level E pass
+    and the S pass cost grow with the candidate pairs per row, which the headline mixture (spread 10) keeps at 1.0;
+    the reference's cost does not depend on the data (src/cluster.cpp:75-79,120-121)."""
+    mu, L, w = mixture_params(D, K, False, spread)
+    mu_t = torch.tensor(mu, dtype=torch.float32, device=dev)
+    L_t = torch.tensor(L, dtype=torch.float32, device=dev)
+    w_t = torch.tensor(w, dtype=torch.float32, device=dev)
+    X = torch.empty(rows, D, dtype=torch.float32, device=dev)
+    z = torch.empty(rows, dtype=torch.int32, device=dev)
+    for c, o in enumerate(range(0, rows, CHUNK)):
+        n = min(CHUNK, rows - o)
+        xc, zc = gen_chunk_torch(torch, dev, 100000 + c, n, D, K, mu_t, L_t, w_t)
+        X[o:o + n] = xc
+        z[o:o + n] = zc
+    torch.cuda.synchronize()
+    eng = lc.Engine(dev.index or 0, lc.F32)
+    eng.set_data_device(X.data_ptr(), rows, D, D)
+    eng.model_init(lc.BGMM)
+    eng.set_labels_device(z.data_ptr(), K)
+    for _ in range(warmup):
+        eng.vbem_step()
+    ms = s_ms = e_ms = 0.0
+    pairs, paths, F = 0, [], None
+    for _ in range(steps):
+        F = eng.vbem_step()
+        t = eng.step_timing()
+        ms += t["step_ms"]; s_ms += t["sstat_ms"]; e_ms += t["estep_ms"]
+        d = eng.estep_detail()
+        pairs += d["pairs"]
+        paths.append(d["path"])
+    eng.close()
+    del X, z
+    torch.cuda.empty_cache()
+    name = {0: "dense", 1: "two-level", 2: "two-level abandoned -> dense"}
+    return {"spread": spread, "rows": rows, "value": rows / (ms / steps * 1e-3), "ms_per_step": ms / steps,
+            "sstat_ms": s_ms / steps, "estep_ms": e_ms / steps, "candidate_pairs_per_row": pairs / steps / rows,
+            "estep_path": name.get(paths[-1], str(paths[-1])), "F_last": F}
+
+
 # ----------------------------------------------------------------- main ---
 def main():
     a = parse()
@@ -268,7 +316,7 @@ def main():
         eng.comm_init_nccl(bytes(idt.cpu().numpy().tobytes()), rank, world)
 
     diag = a.model == "dgmm"
-    mu, L, w = mixture_params(D, K, diag)
+    mu, L, w = mixture_params(D, K, diag, a.spread)
     mu_t = torch.tensor(mu, dtype=torch.float32, device=dev)
     L_t = torch.tensor(L, dtype=torch.float32, device=dev)
     w_t = torch.tensor(w, dtype=torch.float32, device=dev)
@@ -358,6 +406,17 @@ def main():
                          "E-pass kernel; the fp16 hi/lo scheme executes 3 x 0.56 x 2 = 3.4 tensor flop per algorithmic "
                          "flop, so tensor-pipe utilisation is higher than frac (ncu: profiles/)")}
 
+    # ---- soft regime: the same step on overlapping mixtures (N=1 only) -------
+    soft = None
+    if rank == 0 and world == 1 and tc and a.soft_spreads != "none":
+        spreads = SOFT_SPREADS if a.soft_spreads == "auto" else [float(v) for v in a.soft_spreads.split(",") if v]
+        soft = []
+        for sp in spreads:
+            try:
+                soft.append(soft_point(torch, lc, dev, D, K, min(a.soft_rows, N), sp))
+            except Exception as ex:  # noqa: BLE001
+                soft.append({"spread": sp, "error": str(ex)[:200]})
+
     # ---- e2e: the same step through the C ABI from HOST buffers ---------------
     e2e = None
     if not a.no_e2e:
@@ -390,6 +449,10 @@ def main():
                        "timing": "CUDA events on the engine stream around each step, summed, max over ranks",
                        "wall_ms_per_step": wall_ms / a.steps, "F_last": Fs[-1]},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            # flat copies of what characterises the data-dependent part of the step
+            "candidate_pairs_per_row": (levels or {}).get("candidate_pairs_per_row"),
+            "estep_path": "two-level" if two_level else "dense",
+            "spread": a.spread, "soft_regime": soft,
         }
         print(json.dumps(line), flush=True)
     eng.close()
@@ -398,21 +461,25 @@ def main():
 
 
 def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
-    """Every step: host fp64 X (page-locked) -> lcb_set_data -> labels H2D -> one VB iteration -> F on the host."""
+    """Every step, through the C ABI from HOST buffers: host fp64 X (page-locked) -> lcb_set_data -> labels H2D ->
+    one VB iteration -> F on the host -> qZ (fp64, row-major, the caller's matrix: what every learnXXX returns,
+    src/cluster.cpp:661,692,723) back on the host.  `value` includes the qZ emit; `iteration_only_value` stops at F."""
     import psutil
     need = nloc * D * 8
-    if psutil.virtual_memory().available < 1.5 * need + (8 << 30):
-        raise RuntimeError("not enough host memory for a %d-byte page-locked copy of X" % need)
+    need_q = nloc * K * 8
+    if psutil.virtual_memory().available < 1.3 * (need + need_q) + (8 << 30):
+        raise RuntimeError("not enough host memory for page-locked copies of X (%d bytes) and qZ (%d bytes)" % (need, need_q))
     Xh = torch.empty(nloc, D, dtype=torch.float64, pin_memory=True)
     step = 1 << 20
     for r in range(0, nloc, step):
         Xh[r:r + step].copy_(X[r:r + step].double())
     zh = torch.empty(nloc, dtype=torch.int32, pin_memory=True)
     zh.copy_(z)
+    qh = torch.empty(nloc, K, dtype=torch.float64, pin_memory=True)
     torch.cuda.synchronize()
-    Xn = Xh.numpy()
+    Xn, qn = Xh.numpy(), qh.numpy()
     zd = torch.empty(nloc, dtype=torch.int32, device=dev)
-    times = []
+    times, times_it = [], []
     for i in range(1 + a.e2e_steps):
         torch.cuda.synchronize()
         if world > 1:
@@ -425,15 +492,22 @@ def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
         eng.set_labels_device(zd.data_ptr(), K)
         F = eng.vbem_step()
         t1 = time.perf_counter()
+        eng.qZ(0, out=qn)
+        t2 = time.perf_counter()
         if i > 0:
-            times.append(t1 - t0)
-    t = torch.tensor([float(np.mean(times))], dtype=torch.float64, device=dev)
+            times.append(t2 - t0)
+            times_it.append(t1 - t0)
+    rowsum_err = float(np.abs(qn[: 1 << 16].sum(1) - 1.0).max())
+    t = torch.tensor([float(np.mean(times)), float(np.mean(times_it))], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    sec = float(t.item())
+    sec, sec_it = [float(v) for v in t.tolist()]
     return {"value": N / sec, "unit": "points/s", "h2d_bytes_per_step": int(need + nloc * 4),
-            "d2h_bytes_per_step": 8, "ms_per_step": sec * 1e3, "steps": a.e2e_steps,
-            "path": "Engine.set_data(host fp64) + set_labels + lcb_vbem_step through the C ABI", "F": F}
+            "d2h_bytes_per_step": int(need_q + 8), "ms_per_step": sec * 1e3, "steps": a.e2e_steps,
+            "iteration_only_value": N / sec_it, "iteration_only_ms": sec_it * 1e3, "iteration_only_d2h_bytes": 8,
+            "qz_rowsum_max_err": rowsum_err,
+            "path": "Engine.set_data(host fp64) + set_labels + lcb_vbem_step + lcb_get_qz (fp64, row-major, "
+                    "page-locked destination) through the C ABI", "F": F}
 
 
 if __name__ == "__main__":

@@ -49,6 +49,10 @@ class WeightDist {
   const Eigen::ArrayXd& Elogweight() const { return Elogpi_; }
   const Eigen::ArrayXd& getNk() const { return Nk_; }
   double fenergy() const { return lcb_weights_fenergy(h_); }
+  // The prior this object was constructed with (Dirichlet's alpha / StickBreak's concentration; the default
+  // constructors use APRIOR / ALPHA2PRIOR = 1).  Not in the reference's interface: its fits read the private prior
+  // fields of the objects they are handed (src/cluster.cpp:653,684), this header hands the value to the engine.
+  double prior() const { return prior_ > 0 ? prior_ : 1.0; }
   virtual ~WeightDist() { lcb_weights_destroy(h_); }
   WeightDist(const WeightDist& o) : kind_(o.kind_), prior_(o.prior_) { create(); if (o.Nk_.size() > 0 && o.updated_) update(o.Nk_); }
   WeightDist& operator=(const WeightDist& o) {

@@ -8,6 +8,8 @@
 #define LCB200_LIBCLUSTER_H
 
 #include <Eigen/Dense>
+#include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <stdexcept>
 #include <vector>
@@ -27,12 +29,44 @@ const double ZEROCUTOFF = 0.1f;
 typedef std::vector<Eigen::MatrixXd> vMatrixXd;
 typedef std::vector<std::vector<Eigen::MatrixXd> > vvMatrixXd;
 
+// Device arithmetic and device ordinal of the fits started through this header.  The reference API is fp64
+// throughout; the engine's measured path is LCB_F32 (1e-5 on qZ and F).  Compile with
+// -DLCB200_SHIM_PRECISION=LCB_F64 (or run with LCB_SHIM_PRECISION=f64 / LCB_SHIM_DEVICE=<n> in the environment)
+// for the fp64 kernels or another GPU.
+#ifndef LCB200_SHIM_PRECISION
+#define LCB200_SHIM_PRECISION LCB_F32
+#endif
+#ifndef LCB200_SHIM_DEVICE
+#define LCB200_SHIM_DEVICE 0
+#endif
+
 namespace detail {
 struct EngineGuard {
   lcb_engine* e;
-  EngineGuard() : e(nullptr) { distributions::detail::raise(lcb_create(&e, 0, LCB_F32)); }
+  EngineGuard() : e(nullptr) {
+    int prec = LCB200_SHIM_PRECISION, dev = LCB200_SHIM_DEVICE;
+    if (const char* p = std::getenv("LCB_SHIM_PRECISION")) prec = (!std::strcmp(p, "f64") || !std::strcmp(p, "F64")) ? LCB_F64 : LCB_F32;
+    if (const char* d = std::getenv("LCB_SHIM_DEVICE")) dev = std::atoi(d);
+    distributions::detail::raise(lcb_create(&e, dev, prec));
+  }
   ~EngineGuard() { lcb_destroy(e); }
 };
+
+// The weight prior the fit runs with.  cluster<W,C>() keeps the prior of every weight object the caller passes and
+// appends default-constructed ones up to J (weights.resize(J, W()), src/cluster.cpp:192; the single-group wrappers
+// pass their argument, :653,684,715).  The engine takes one prior for all groups: the callers' objects must agree
+// (an empty vector means the default prior).
+template <class W>
+double common_weight_prior(const std::vector<W>& weights, int J) {
+  if (weights.empty()) return -1.0;
+  const double p0 = weights[0].prior();
+  for (size_t j = 1; j < weights.size() && (int)j < J; ++j)
+    if (weights[j].prior() != p0)
+      throw std::invalid_argument("the device engine takes one weight prior for all groups");
+  if ((int)weights.size() < J && p0 != W().prior())
+    throw std::invalid_argument("the device engine takes one weight prior for all groups");
+  return p0;
+}
 
 // Runs cluster<W,C>() on the device and rebuilds the caller's objects from the
 // engine's statistics: qZ, weights (one per group) and clusters.
@@ -53,12 +87,13 @@ double fit(int model, const vMatrixXd& X, vMatrixXd& qZ, std::vector<W>& weights
     Nj[j] = X[j].rows();
     ld[j] = distributions::detail::ld_of(X[j]);
   }
+  const double wprior = common_weight_prior(weights, J);
   EngineGuard g;
   const int layout = Eigen::MatrixXd::IsRowMajor ? LCB_ROW_MAJOR : LCB_COL_MAJOR;
   raise(lcb_set_data(g.e, J, ptr.data(), Nj.data(), D, ld.data(), layout));
   double F = 0;
   int K = 0;
-  raise(lcb_learn(g.e, model, clusterprior, -1.0, maxclusters, sparse, verbose, nthreads, &F, &K));
+  raise(lcb_learn(g.e, model, clusterprior, wprior, maxclusters, sparse, verbose, nthreads, &F, &K));
   qZ.resize(J);
   weights.resize(J, W());
   for (int j = 0; j < J; ++j) {

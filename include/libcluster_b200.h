@@ -74,8 +74,8 @@ int lcb_set_data_device_f32(lcb_engine *e, const float *X_dev, int64_t N, int D,
                             const int32_t *gid_dev, int J);
 
 /* The model-selection fit: cluster<W,C>() (src/cluster.cpp:564-629) behind
- * learnVDP/BGMM/DGMM/GMC/SGMC/DGMC (:636-831).  weight_prior <= 0 means a
- * default-constructed weight object (StickBreak()/Dirichlet()); nthreads has
+ * learnVDP/BGMM/DGMM/GMC/SGMC/DGMC (:636-831).  weight_prior < 0 means a
+ * default-constructed weight object (StickBreak()/Dirichlet()), 0 is LCB_EINVAL; nthreads has
  * no meaning on the GPU but nthreads < 1 is still LCB_EINVAL (:576-577). */
 int lcb_learn(lcb_engine *e, int model, double clusterprior, double weight_prior, int maxclusters,
               int sparse, int verbose, unsigned nthreads, double *F, int *K);
@@ -149,7 +149,8 @@ int lcb_comm_init_host(lcb_engine *e, lcb_allreduce_fn fn, void *ctx, int rank, 
 
 /* ---------------------------------------------- operator surface (L1) ----
  * WeightDist: update / Elogweight / getNk / fenergy (distributions.h:60-97).
- * prior <= 0 selects the default constructor. Host-side, K-length math. */
+ * prior < 0 selects the default constructor, prior == 0 is LCB_EINVAL (distributions.cpp:107,234).
+ * Host-side, K-length math. */
 int lcb_weights_create(lcb_weights **out, int kind, double prior);
 void lcb_weights_destroy(lcb_weights *w);
 int lcb_weights_update(lcb_weights *w, const double *Nk, int K);

@@ -166,12 +166,17 @@ class Engine:
     def J(self):
         return nat.lib().lcb_num_groups(self._h)
 
-    def qZ(self, j=None, order="C"):
+    def qZ(self, j=None, order="C", out=None):
+        """qZ of group j as float64 [N_j x K].  `out`: an existing array of that shape and order to fill (a page-locked
+        row-major one is written by DMA straight from the device)."""
         if j is None:
             return [self.qZ(g, order) for g in range(self.J)]
         Nj = int(nat.lib().lcb_num_rows(self._h, j))
         K = self._qcols()
-        out = np.zeros((Nj, K), order=order)
+        if out is None:
+            out = np.empty((Nj, K), order=order)
+        elif out.shape != (Nj, K) or out.dtype != np.float64 or not (out.flags.c_contiguous if order == "C" else out.flags.f_contiguous):
+            raise InvalidArgument("qZ: out must be a float64 array of shape (%d, %d) in order %s" % (Nj, K, order))
         lay = nat.ROW_MAJOR if order == "C" else nat.COL_MAJOR
         nat.check(nat.lib().lcb_get_qz(self._h, j, _dp(out), max(K if order == "C" else Nj, 1), lay))
         return out

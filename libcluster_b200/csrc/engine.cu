@@ -1720,6 +1720,12 @@ void Engine::get_step_timing(double out[4]) {
 }
 
 // ---------------------------------------------------------------- results ---
+// qZ of group j in the caller's layout as doubles (cluster.cpp:661,692,723: every entry point returns qZ).  The
+// emit pass is bound by the PCIe link, so it is pipelined:
+//  * row-major into page-locked memory: fp32 -> fp64 on the device into two alternating buffers, each DMA'd straight
+//    into the caller's matrix by a copy stream while the next chunk converts;
+//  * otherwise: the engine's element type crosses the link (4 bytes per value in LCB_F32) into two page-locked
+//    staging buffers and the host's threads widen / transpose chunk i into `out` while chunk i + 1 is in flight.
 void Engine::get_qz(int j, double* out, int64_t ld, int layout) {
   if (j < 0 || j >= main_.J || out == nullptr) throw_invalid("get_qz: bad group");
   check(cudaSetDevice(device_), "cudaSetDevice");
@@ -1728,25 +1734,102 @@ void Engine::get_qz(int j, double* out, int64_t ld, int layout) {
   for (int g = 0; g < j; ++g) off += Nj_[g];
   const int64_t Nj = Nj_[j];
   if (ld < (layout == 0 ? K : Nj)) throw_invalid("get_qz: leading dimension too small");
-  const int64_t chunk = std::max<int64_t>(1, (int64_t)(16u << 20) / (8 * (int64_t)std::max(K, 1)));
-  reserve(d_tmp_, sizeof(double) * chunk * K);
-  double* h = (double*)pinned(sizeof(double) * chunk * K);
-  for (int64_t r = 0; r < Nj; r += chunk) {
-    const int64_t rows = std::min(chunk, Nj - r);
-    if (prec_ == kF32)
-      check(dev::q_to_double<float>(stream_, (const float*)main_.q + (off + r) * main_.ldq, main_.ldq, rows, K,
-                                    (double*)d_tmp_.p, K, 0), "q_to_double");
-    else
-      check(dev::q_to_double<double>(stream_, (const double*)main_.q + (off + r) * main_.ldq, main_.ldq, rows, K,
-                                     (double*)d_tmp_.p, K, 0), "q_to_double");
-    check(cudaMemcpyAsync(h, d_tmp_.p, sizeof(double) * rows * K, cudaMemcpyDeviceToHost, stream_), "D2H q");
-    sync();
-    for (int64_t n = 0; n < rows; ++n)
-      for (int k = 0; k < K; ++k) {
-        if (layout == 0) out[(r + n) * ld + k] = h[n * K + k];
-        else out[(int64_t)k * ld + r + n] = h[n * K + k];
-      }
+  if (Nj <= 0 || K <= 0) return;
+  const size_t es = prec_ == kF32 ? 4 : 8;
+  bool pinned_dst = false;
+  if (layout == 0) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, out) == cudaSuccess) pinned_dst = at.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
   }
+  struct Res {
+    cudaStream_t cs = nullptr;
+    cudaEvent_t a[2] = {nullptr, nullptr}, b[2] = {nullptr, nullptr};
+    ~Res() {
+      for (int i = 0; i < 2; ++i) {
+        if (a[i]) cudaEventDestroy(a[i]);
+        if (b[i]) cudaEventDestroy(b[i]);
+      }
+      if (cs) cudaStreamDestroy(cs);
+    }
+  } r;
+  for (int i = 0; i < 2; ++i) {
+    check(cudaEventCreateWithFlags(&r.a[i], cudaEventDisableTiming), "event");
+    check(cudaEventCreateWithFlags(&r.b[i], cudaEventDisableTiming), "event");
+  }
+  if (pinned_dst) {
+    const int64_t chunk = std::max<int64_t>(1, (int64_t)(64u << 20) / (8 * (int64_t)K));
+    reserve(d_tmp_, 2 * sizeof(double) * (size_t)chunk * K);
+    check(cudaStreamCreateWithFlags(&r.cs, cudaStreamNonBlocking), "stream");
+    int64_t i = 0;
+    for (int64_t r0 = 0; r0 < Nj; r0 += chunk, ++i) {
+      const int slot = (int)(i & 1);
+      const int64_t rows = std::min(chunk, Nj - r0);
+      double* dbuf = (double*)d_tmp_.p + (size_t)slot * chunk * K;
+      if (i >= 2) check(cudaStreamWaitEvent(stream_, r.b[slot], 0), "wait");
+      if (prec_ == kF32)
+        check(dev::q_to_double<float>(stream_, (const float*)main_.q + (off + r0) * main_.ldq, main_.ldq, rows, K, dbuf, K, 0), "q_to_double");
+      else
+        check(dev::q_to_double<double>(stream_, (const double*)main_.q + (off + r0) * main_.ldq, main_.ldq, rows, K, dbuf, K, 0), "q_to_double");
+      check(cudaEventRecord(r.a[slot], stream_), "event");
+      check(cudaStreamWaitEvent(r.cs, r.a[slot], 0), "wait");
+      check(cudaMemcpy2DAsync(out + r0 * ld, sizeof(double) * (size_t)ld, dbuf, sizeof(double) * (size_t)K,
+                              sizeof(double) * (size_t)K, (size_t)rows, cudaMemcpyDeviceToHost, r.cs), "D2H q");
+      check(cudaEventRecord(r.b[slot], r.cs), "event");
+    }
+    check(cudaStreamSynchronize(r.cs), "sync");
+    sync();
+    return;
+  }
+  const int64_t chunk = std::max<int64_t>(1, (int64_t)(32u << 20) / ((int64_t)es * K));
+  unsigned char* h = (unsigned char*)pinned(2 * es * (size_t)chunk * K);
+  const int64_t nchunks = (Nj + chunk - 1) / chunk;
+  auto widen = [&](int64_t c) {
+    const int64_t r0 = c * chunk, rows = std::min(chunk, Nj - r0);
+    const unsigned char* hs = h + (size_t)(c & 1) * es * (size_t)chunk * K;
+    const int64_t nblk = (rows + 255) / 256;
+#pragma omp parallel for schedule(static) num_threads(host_threads_) if (rows * K > 65536)
+    for (int64_t b = 0; b < nblk; ++b) {
+      const int64_t n0 = b * 256, n1 = std::min(rows, n0 + 256);
+      if (layout == 0) {
+        for (int64_t n = n0; n < n1; ++n) {
+          double* dst = out + (r0 + n) * ld;
+          if (prec_ == kF32) {
+            const float* src = (const float*)hs + n * K;
+            for (int k = 0; k < K; ++k) dst[k] = (double)src[k];
+          } else {
+            std::memcpy(dst, (const double*)hs + n * K, sizeof(double) * (size_t)K);
+          }
+        }
+      } else {
+        for (int k = 0; k < K; ++k) {
+          double* dst = out + (int64_t)k * ld + r0;
+          if (prec_ == kF32) {
+            const float* src = (const float*)hs + k;
+            for (int64_t n = n0; n < n1; ++n) dst[n] = (double)src[n * K];
+          } else {
+            const double* src = (const double*)hs + k;
+            for (int64_t n = n0; n < n1; ++n) dst[n] = src[n * K];
+          }
+        }
+      }
+    }
+  };
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int slot = (int)(c & 1);
+    const int64_t r0 = c * chunk, rows = std::min(chunk, Nj - r0);
+    // slot `slot` was widened two rounds ago (widen(c - 2) ran before this copy is issued)
+    check(cudaMemcpy2DAsync(h + (size_t)slot * es * (size_t)chunk * K, es * (size_t)K,
+                            (const unsigned char*)main_.q + es * (size_t)((off + r0) * main_.ldq), es * (size_t)main_.ldq,
+                            es * (size_t)K, (size_t)rows, cudaMemcpyDeviceToHost, stream_), "D2H q");
+    check(cudaEventRecord(r.a[slot], stream_), "event");
+    if (c > 0) {
+      check(cudaEventSynchronize(r.a[slot ^ 1]), "event sync");
+      widen(c - 1);
+    }
+  }
+  check(cudaEventSynchronize(r.a[(nchunks - 1) & 1]), "event sync");
+  widen(nchunks - 1);
 }
 
 void Engine::get_group_weights(int j, double* Nk, double* Elogw, double* fen) {

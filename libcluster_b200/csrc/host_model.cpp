@@ -46,6 +46,9 @@ void model_kinds(int model, int* wkind, int* ckind) {
 // ---------------------------------------------------------------- weights --
 WeightPost::WeightPost(int kind, double prior) : kind_(kind) {
   if (kind < 0 || kind > 2) throw_invalid("unknown weight distribution kind");
+  // prior < 0 (or NaN) is the sentinel of the default constructors; an explicit 0 is the reference's error
+  // (distributions.cpp:107-108, :234-235)
+  if (prior == 0) throw_invalid(kind == kDirichlet ? "Alpha prior must be > 0!" : "Concentration parameter has to be > 0!");
   a1p_ = prior > 0 ? prior : kAlpha1Prior;
   a2p_ = kAlpha2Prior;
   Fp_ = std::lgamma(a1p_) + std::lgamma(a2p_) - std::lgamma(a1p_ + a2p_);

@@ -176,8 +176,11 @@ __global__ void __launch_bounds__(kNT) mstep_cluster_kernel(MStepArgs a, int wor
       for (int p = j + 1 + tid; p < D; p += kNT) col[p] = A[(size_t)p * lda + j];
       __syncthreads();
       const double dinv = 1.0 / Ld[j];
-      for (int r = tid; r < 2 * (D - 1 - j) + 2; r += kNT) {
-        const int i = j + 1 + (r >> 1), h = r & 1;  // the pair (2 lanes) of row i; pads to keep the shuffle converged
+      // the trip count is rounded up to whole warps: every lane of a warp that enters reaches the full-mask shuffle
+      // (lanes past the last row carry acc = 0); a partial warp at the shuffle deadlocks
+      const int rcount = (2 * (D - 1 - j) + 2 + 31) & ~31;
+      for (int r = tid; r < rcount; r += kNT) {
+        const int i = j + 1 + (r >> 1), h = r & 1;  // the pair (2 lanes) of row i
         double acc = 0;
         if (i < D) {
           const double* row = A + (size_t)i * lda;

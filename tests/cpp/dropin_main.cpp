@@ -59,6 +59,19 @@ int main(int argc, char** argv) {
       rowsum += s;
     }
     cout << "BGMM F " << F2 << " K " << cl2.size() << " rowsum " << rowsum << endl;
+    // caller-supplied weight priors are kept by the fit (src/cluster.cpp:653,684)
+    {
+      Dirichlet dir5(5.0);
+      vector<GaussWish> cl3;
+      MatrixXd q3;
+      double F3 = learnBGMM(Xcat, q3, dir5, cl3, PRIORVAL, -1, false, 1);
+      cout << "BGMM5 F " << F3 << " K " << cl3.size() << " Elogw " << dir5.Elogweight().transpose() << endl;
+      StickBreak sb3(3.0);
+      vector<GaussWish> cl4;
+      MatrixXd q4;
+      double F4 = learnVDP(Xcat, q4, sb3, cl4, PRIORVAL, -1, false, 1);
+      cout << "VDP3 F " << F4 << " K " << cl4.size() << " Elogw " << sb3.Elogweight().transpose() << endl;
+    }
     // operator surface
     GaussWish c(PRIORVAL, (unsigned)D);
     c.addobs(VectorXd::Ones(Xcat.rows()), Xcat);

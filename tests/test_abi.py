@@ -52,6 +52,11 @@ def test_weight_posteriors(kind, cls, K):
         assert w.fenergy() == pytest.approx(o.fenergy(), rel=1e-11, abs=1e-11)
     with pytest.raises(lc.InvalidArgument):
         cls(-2.0)
+    # C ABI: a negative prior is the "default constructor" sentinel, an explicit 0 is the reference's invalid_argument
+    import ctypes as C
+    h = C.c_void_p()
+    assert nat.lib().lcb_weights_create(C.byref(h), kind, C.c_double(0.0)) == 1  # LCB_EINVAL
+    assert b"> 0" in nat.lib().lcb_last_error()
 
 
 @pytest.mark.parametrize("kind,cls", [(po.C_GAUSSWISH, lc.GaussWish), (po.C_NORMGAMMA, lc.NormGamma)])

@@ -42,6 +42,18 @@ def test_cpp_user_program_runs_on_the_engine(tmp_path, testdata):
     assert m and int(m.group(2)) == 3 and float(m.group(1)) == pytest.approx(float(g2["F"]), rel=1e-5)
     assert float(m.group(3)) == pytest.approx(120.0, abs=1e-3)
     Xcat = np.concatenate(list(X), 0)
+    # a caller's Dirichlet(5.0) / StickBreak(3.0) prior reaches the fit (src/cluster.cpp:653,684)
+    for tag, model, wp in (("BGMM5", po.BGMM, 5.0), ("VDP3", po.VDP, 3.0)):
+        mo = po.Model(model, [Xcat])
+        Fo = mo.learn(weight_prior=wp)
+        m = re.search(tag + r" F (\S+) K (\d+) Elogw (.*)", out)
+        assert m, out
+        assert int(m.group(2)) == mo.K
+        assert float(m.group(1)) == pytest.approx(Fo, rel=1e-5)
+        elw = np.array([float(v) for v in m.group(3).split()])
+        assert np.allclose(elw, mo.weights(0)[0], atol=1e-4)
+        # and the prior matters on this data: the default-prior fit has a different F
+        assert abs(Fo - po.Model(model, [Xcat]).learn()) > 1e-4 * abs(Fo)
     c = po.Cluster(po.C_GAUSSWISH, 1.0, 2)
     c.addobs(np.ones(120), Xcat)
     c.update()
