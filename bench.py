@@ -29,7 +29,8 @@ sys.path.insert(0, ROOT)
 
 CHUNK = 250_000          # rows per generation chunk; shards are whole chunks
 SEED = 20260925
-SOFT_SPREADS = [1.0, 0.5]   # means U(-s, s)^D of the extra soft-regime points (see soft_point)
+SOFT_SPREADS = [0.65, 0.3]  # means U(-s, s)^D of the extra soft-regime points: about 4 and 17 candidate pairs per row
+                            # (profiles/soft_sweep_r02_4m.log)
 # fallback only if MEASURED_PEAKS.json is absent (/opt/skills/guides/B200_PROFILING.md)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
@@ -44,7 +45,15 @@ def parse():
     ap.add_argument("--dim", type=int, default=128)
     ap.add_argument("--clusters", type=int, default=64)
     ap.add_argument("--precision", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--model", default="bgmm", choices=["bgmm", "dgmm"], help="bgmm: full covariance (headline); dgmm: diagonal (config 5)")
+    ap.add_argument("--model", default="bgmm", choices=["bgmm", "dgmm", "gmc"],
+                    help="bgmm: full covariance (headline); dgmm: diagonal (config 5); gmc: grouped, GDirichlet weights per "
+                         "group and shared GaussWish clusters, whole groups per rank (config 4: --groups 256 --n-points "
+                         "25600000 --dim 64 --clusters 64)")
+    ap.add_argument("--groups", type=int, default=256, help="groups of --model gmc (rows are split evenly over them)")
+    ap.add_argument("--fit", action="store_true",
+                    help="config 3: time a whole learnVDP fit from K = 1 with greedy splits (lcb_learn) instead of "
+                         "steady-state iterations; prints fit seconds, final K and F")
+    ap.add_argument("--weak", action="store_true", help="weak scaling: --n-points rows per GPU instead of in total")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -301,10 +310,17 @@ def main():
     torch.cuda.set_device(dev)
 
     N, D, K = a.n_points, a.dim, a.clusters
+    if a.weak:
+        N *= world
     prec = lc.F32 if a.precision == "f32" else lc.F64
-    nchunks = (N + CHUNK - 1) // CHUNK
+    grouped = a.model == "gmc"
+    J = a.groups if grouped else 1
+    chunk = (N // J) if grouped else CHUNK          # grouped: one generation chunk per group, whole groups per rank
+    if grouped and (N % J or J % world):
+        raise SystemExit("--model gmc needs n-points divisible by --groups and --groups divisible by the GPUs")
+    nchunks = (N + chunk - 1) // chunk
     c0, c1 = lc.shard_rows(nchunks, rank, world)
-    r0, r1 = c0 * CHUNK, min(N, c1 * CHUNK)
+    r0, r1 = c0 * chunk, min(N, c1 * chunk)
     nloc = r1 - r0
 
     eng = lc.Engine(local, prec)
@@ -322,16 +338,24 @@ def main():
     w_t = torch.tensor(w, dtype=torch.float32, device=dev)
     X = torch.empty(nloc, D, dtype=torch.float32, device=dev)
     z = torch.empty(nloc, dtype=torch.int32, device=dev)
+    gid = torch.empty(nloc, dtype=torch.int32, device=dev) if grouped else None
     for c in range(c0, c1):
-        rows = min(CHUNK, N - c * CHUNK)
-        xc, zc = gen_chunk_torch(torch, dev, c, rows, D, K, mu_t, L_t, w_t)
-        o = c * CHUNK - r0
+        rows = min(chunk, N - c * chunk)
+        wc = w_t
+        if grouped:   # per-group mixing weights Dirichlet(0.5) over the shared clusters
+            wc = torch.tensor(np.random.default_rng(SEED + 1000 + c).dirichlet(0.5 * np.ones(K)), dtype=torch.float32, device=dev)
+        xc, zc = gen_chunk_torch(torch, dev, c, rows, D, K, mu_t, L_t, wc)
+        o = c * chunk - r0
         X[o:o + rows] = xc
         z[o:o + rows] = zc
+        if grouped:
+            gid[o:o + rows] = c
     torch.cuda.synchronize()
 
-    MODEL = lc.DGMM if diag else lc.BGMM
-    eng.set_data_device(X.data_ptr(), nloc, D, D)
+    MODEL = lc.DGMM if diag else lc.GMC if grouped else lc.BGMM
+    if a.fit:
+        return run_fit(torch, dist, lc, eng, X, N, nloc, D, world, rank, dev, a)
+    eng.set_data_device(X.data_ptr(), nloc, D, D, gid.data_ptr() if grouped else None, J)
     eng.model_init(MODEL)
     eng.set_labels_device(z.data_ptr(), K)
 
@@ -373,7 +397,7 @@ def main():
 
     # ---- roofline of the dominant kernel (device-event time, this run) -------
     pk = peaks()
-    tc = (prec == lc.F32 and D == 128 and not diag and not os.environ.get("LCB_DISABLE_TC"))
+    tc = (prec == lc.F32 and D in (64, 128) and not diag and not os.environ.get("LCB_DISABLE_TC"))
     flops_half = (3.5 * K * D * nloc) if diag else float(K) * D * D * nloc          # algorithmic flops of either half per launch (2KD^2 total)
     levels = None
     if two_level and coarse_ms >= s_ms:
@@ -382,13 +406,13 @@ def main():
         kname, kms = "estep_coarse_tc128_kernel", coarse_ms / a.steps
         # ncu --set full at N=4M (profiles/ncu_r01_coarse_v4_raw.csv): dram read 2.12 GB + write 1.07 GB per launch
         # = 799 B / point (algorithmic: 512 B of X, 256 B of level-1 bounds, 8 B of candidate mask)
-        traffic = 799.0 * nloc
+        traffic = 799.0 * nloc if D == 128 else None
         levels = {k_: (lv[k_] / a.steps) for k_ in ("coarse_ms", "lists_ms", "refine_ms", "finalize_ms")}
         levels["candidate_pairs_per_row"] = lv["pairs"] / a.steps / max(nloc, 1)
     elif e_ms >= s_ms:
         kname, kms = ("estep_tc128_kernel" if tc else "estep_full_kernel"), e_ms / a.steps
         # measured with ncu --set full at N=2M (profiles/ncu_r01_tc_summary.md): dram read+write per point
-        traffic = 756.0 * nloc if tc else None
+        traffic = 756.0 * nloc if (tc and D == 128) else None
     else:
         kname, kms = ("nz_count+nz_fill+sstat_tc128_kernel" if tc else "sstat pass"), s_ms / a.steps
         traffic = None
@@ -408,7 +432,7 @@ def main():
 
     # ---- soft regime: the same step on overlapping mixtures (N=1 only) -------
     soft = None
-    if rank == 0 and world == 1 and tc and a.soft_spreads != "none":
+    if rank == 0 and world == 1 and tc and D == 128 and K == 64 and a.soft_spreads != "none":
         spreads = SOFT_SPREADS if a.soft_spreads == "auto" else [float(v) for v in a.soft_spreads.split(",") if v]
         soft = []
         for sp in spreads:
@@ -419,7 +443,7 @@ def main():
 
     # ---- e2e: the same step through the C ABI from HOST buffers ---------------
     e2e = None
-    if not a.no_e2e:
+    if not a.no_e2e and not grouped:
         try:
             e2e = run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a)
         except Exception as ex:  # noqa: BLE001
@@ -438,12 +462,14 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "VB E-step points/sec at N=50M D=128 K=64", "value": value, "unit": "points/s",
+            "metric": "VB E-step points/sec at N=%s D=%d K=%d" % (
+                "50M" if N == 50_000_000 else str(N), D, K), "value": value, "unit": "points/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak" if a.weak else "strong", "vs_baseline": None,
             "dtype": "f32" if prec == lc.F32 else "f64", "data": "synthetic",
             "config": {"workload": "VB iteration (SS + M + E + F), %s, N=%d D=%d K=%d" % (
                 "learnDGMM pair (Dirichlet, NormGamma diagonal)" if diag else
+                ("learnGMC pair (GDirichlet per group, shared GaussWish), J=%d groups, whole groups per rank" % J) if grouped else
                 "learnBGMM pair (Dirichlet, GaussWish full-cov)", N, D, K), "rows_per_gpu": nloc, "parallelism": "rows sharded x%d" % world,
                        "l2": "inputs (%.1f GB/GPU) far larger than L2" % (nloc * D * 4 / 1e9),
                        "timing": "CUDA events on the engine stream around each step, summed, max over ranks",
@@ -455,6 +481,34 @@ def main():
             "spread": a.spread, "soft_regime": soft,
         }
         print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_fit(torch, dist, lc, eng, X, N, nloc, D, world, rank, dev, a):
+    """Config 3: a whole learnVDP fit (cluster<StickBreak,GaussWish>, src/cluster.cpp:564-629) on the resident rows:
+    K = 1, VB to convergence, greedy split search, ... until no split lowers F.  Wall time of lcb_learn."""
+    eng.set_data_device(X.data_ptr(), nloc, D, D)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    F = eng.learn(lc.VDP, maxclusters=a.clusters if a.clusters > 0 else -1)
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sec = float(t.item())
+    Ftr, Ktr = eng.trace()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "learnVDP fit seconds at N=%d D=%d (greedy split from K=1)" % (N, D), "value": sec, "unit": "s",
+            "n_gpus": world, "higher_is_better": False, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "learnVDP full fit, N=%d D=%d, true clusters %d, maxclusters %d" % (N, D, a.clusters, a.clusters),
+                       "rows_per_gpu": nloc},
+            "final_K": int(eng.K), "F": F, "vb_iterations": int(len(Ftr)), "points_per_s_per_iteration": N * len(Ftr) / sec,
+        }), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()

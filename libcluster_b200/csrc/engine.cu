@@ -8,6 +8,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <iostream>
 #include <thread>
@@ -82,6 +83,18 @@ int nccl_get_unique_id(char out[128], std::string* err) {
 // ---------------------------------------------------------------- plumbing --
 void Engine::check(cudaError_t e, const char* what) const {
   if (e != cudaSuccess) throw Error{4, std::string(what) + ": " + cudaGetErrorString(e)};
+  if (debug_sync_ && stream_ != nullptr) {
+    // LCB_DEBUG_SYNC=1: wait after every checked call, so that a failing kernel is reported under its own name,
+    // together with the error word the tensor-core kernels leave (0xdead0000 | barrier address: a barrier time-out)
+    const cudaError_t s = cudaStreamSynchronize(stream_);
+    if (s != cudaSuccess) {
+      char buf[64] = "";
+      unsigned w[2] = {0, 0};
+      if (d_err_.p != nullptr && cudaMemcpy(w, d_err_.p, sizeof(w), cudaMemcpyDeviceToHost) == cudaSuccess)
+        std::snprintf(buf, sizeof(buf), " (err words %08x %08x)", w[0], w[1]);
+      throw Error{4, std::string(what) + " [after sync]: " + cudaGetErrorString(s) + buf};
+    }
+  }
 }
 void Engine::sync() {
   ++syncs_;
@@ -102,6 +115,8 @@ Engine::Engine(int device, int precision) : device_(device), prec_(precision) {
   for (auto& e : ev_) check(cudaEventCreate(&e), "cudaEventCreate");
   const char* no_tc = std::getenv("LCB_DISABLE_TC");
   use_tc_ = !(no_tc && no_tc[0] && no_tc[0] != '0');
+  if (const char* ts = std::getenv("LCB_TC_SSTAT")) use_tc_sstat_ = !(ts[0] == '0');
+  if (const char* ds = std::getenv("LCB_DEBUG_SYNC")) debug_sync_ = ds[0] == '1';
   if (const char* tl = std::getenv("LCB_TC_TWO_LEVEL")) {
     if (tl[0]) use_two_level_ = tl[0] != '0';
   }
@@ -1309,7 +1324,9 @@ double Engine::vbem(View& v, std::vector<WeightPost>& weights, std::vector<Clust
   int i = 0, n = 0;
   // The iterations run against the device-resident model (statistics, posteriors and E-step operands never leave
   // the GPU; the host reads one small record per iteration); the host objects are refreshed once at the end.
-  const bool on_device = use_dev_mstep_ && v.N > 0;
+  // every rank must take the same path (the collectives differ): a rank without rows of this view -- the members of
+  // a split candidate can all live elsewhere -- runs the device iteration on zero rows
+  const bool on_device = use_dev_mstep_ && (v.N > 0 || world_ > 1);
   if (on_device) {
     dev_drop();
     dev_begin(v, weights, clusters, hints);
@@ -1664,7 +1681,7 @@ void Engine::vbem_step(double* F) {
   while ((int)clusters_.size() < K) clusters_.emplace_back(ckind_, prior_, main_.D);
   hints_.resize(K);
   v_ntot_ = N_total_;
-  const bool on_device = use_dev_mstep_ && main_.N > 0;
+  const bool on_device = use_dev_mstep_ && (main_.N > 0 || world_ > 1);
   if (on_device && !(dev_live_ && dev_view_ == &main_ && dev_K_ == K)) {
     dev_drop();
     dev_begin(main_, weights_, clusters_, hints_);

@@ -137,6 +137,8 @@ class Engine {
 
   int device_, prec_, sms_;
   bool use_tc_ = true;  // tcgen05 tier of the E step (LCB_DISABLE_TC=1 forces the SIMT tier)
+  bool debug_sync_ = false;   // LCB_DEBUG_SYNC=1: synchronise after every launch (names the failing kernel)
+  bool use_tc_sstat_ = true;  // tcgen05 scatter of the S pass (LCB_TC_SSTAT=0: SIMT gather kernel, for A/B checks)
   // Two-level E step (one-product distances for all pairs, exact logits for the candidates only).
   // LCB_TC_TWO_LEVEL=0/1 overrides the default; LCB_TC_STAGE=coarse|refine stops after that level (tests).
   bool use_two_level_ = true;

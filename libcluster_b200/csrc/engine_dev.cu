@@ -180,8 +180,9 @@ void Engine::dev_sphase(View& v) {
   (void)cld;
   check(cudaMemsetAsync(d_njk, 0, sizeof(double) * (size_t)(nstat + 1), stream_), "memset stats");
   check(cudaEventRecord(ev_[0], stream_), "event");
-  const bool tc_s = full && prec_ == kF32 && use_tc_ && dev::tc_supported(D, v.ldx) && K <= dev::kTcCoarseMaxK;
-  const bool reuse = list_valid_ && list_q_ == v.q && list_K_ == K && list_N_ == v.N && tc_s && J == 1 && !sparse_;
+  const int tdim = dev::tc_dim(D, v.ldx);
+  const bool tc_s = full && prec_ == kF32 && use_tc_ && use_tc_sstat_ && tdim != 0 && K <= dev::kTcCoarseMaxK;
+  const bool reuse = list_valid_ && list_q_ == v.q && list_K_ == K && list_N_ == v.N && tc_s && !sparse_;
   list_valid_ = false;
   const bool fuse_counts = full && !sparse_ && v.N > 0;  // nz_count / gather_list_q produce Njk in the same sweep
   if (!fuse_counts) {
@@ -210,11 +211,12 @@ void Engine::dev_sphase(View& v) {
       const size_t rows_bytes = (size_t)round_up((int64_t)elist_cap_ * 4, 256);
       int32_t* lrow = (int32_t*)d_list_.p;
       float* lq = (float*)((unsigned char*)d_list_.p + rows_bytes);
-      check(dev::gather_list_q(stream_, sms_, (const float*)v.q, v.ldq, lrow, d_koff, d_tot, list_maxcnt_, K, lq, d_njk),
+      check(dev::gather_list_q(stream_, sms_, (const float*)v.q, v.ldq, lrow, d_koff, d_tot, list_maxcnt_, K, lq, d_njk,
+                               v.gid),
             "gather_list_q");
       ++launches_;
       ke = dev::sstat_tc128(stream_, sms_, (const float*)v.X, lrow, lq, d_koff, d_tot, list_maxcnt_, list_nnz_, K,
-                            (const float*)d_cen_.p, 0.f, d_xs, d_S, (unsigned*)d_err_.p, d_sscale, skipS);
+                            (const float*)d_cen_.p, 0.f, d_xs, d_S, (unsigned*)d_err_.p, d_sscale, skipS, tdim);
       ++launches_;
     } else {
       const int64_t nb = dev::nz_blocks(v.N);
@@ -245,7 +247,8 @@ void Engine::dev_sphase(View& v) {
                                   dev::kNzNonZero, skipS), "nz_fill");
         if (tc_s)
           ke = dev::sstat_tc128(stream_, sms_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, (long long)v.N,
-                                nnz_hint, K, (const float*)d_cen_.p, 0.f, d_xs, d_S, (unsigned*)d_err_.p, d_sscale, skipS);
+                                nnz_hint, K, (const float*)d_cen_.p, 0.f, d_xs, d_S, (unsigned*)d_err_.p, d_sscale, skipS,
+                                tdim);
         else
           ke = dev::sstat_gather_full<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
                                              (long long)v.N, K, (const float*)d_cen_.p, d_xs, d_S, skipS);
@@ -283,7 +286,7 @@ void Engine::dev_two_level(View& v, int K, const TcLayout& lay, bool first_try) 
   if (v.xnorm == nullptr && v.N > 0) {
     cudaError_t e = cudaMalloc((void**)&v.xnorm, sizeof(float) * (size_t)v.N);
     if (e != cudaSuccess) throw Error{5, std::string("cudaMalloc: ") + cudaGetErrorString(e)};
-    check(dev::row_norm128(stream_, sms_, (const float*)v.X, v.N, v.xnorm), "row_norm128");
+    check(dev::row_norm128(stream_, sms_, (const float*)v.X, v.N, v.xnorm, dev::tc_dim(v.D, v.ldx)), "row_norm128");
     ++launches_;
   }
   float* q = (float*)v.q;
@@ -306,7 +309,7 @@ void Engine::dev_two_level(View& v, int K, const TcLayout& lay, bool first_try) 
     check(cudaEventRecord(ev_[4], stream_), "event");
     check(dev::estep_coarse_tc128(stream_, sms_, (const float*)v.X, v.xnorm, v.N, v.gid, K, d_blob, d_aug, d_cpar, d_lw,
                                   d_act, sg, 0, kMargin, q, v.ldq, cmask, coarse_sbase_hint_, d_err, ctl + dev::kCtlAugH,
-                                  skip),
+                                  skip, dev::tc_dim(v.D, v.ldx)),
           "estep_coarse_tc128 launch");
     ++launches_;
     check(cudaEventRecord(ev_[5], stream_), "event");
@@ -343,7 +346,9 @@ void Engine::dev_two_level(View& v, int K, const TcLayout& lay, bool first_try) 
   const double limit = 0.4 * (double)K * (double)v.N;
   const long long cap_max = (long long)limit + 1024;
   if (elist_cap_ <= 0) elist_cap_ = std::min<long long>(cap_max, std::max<long long>(2 * (long long)v.N + 1024, (long long)(1.5 * last_pairs_)));
+  if ((long long)v.N * K <= (32LL << 20)) elist_cap_ = std::max(elist_cap_, cap_max);  // small views: room for every pair the pass may keep
   elist_cap_ = std::min(elist_cap_, std::max<long long>(cap_max, 1024));
+  if (tc_stage_ != 0) elist_cap_ = std::max<long long>((long long)v.N * K, 1024);  // test stages keep every candidate
   const size_t rows_bytes = (size_t)round_up((int64_t)elist_cap_ * 4, 256);
   const int64_t items_cap = elist_cap_ / 128 + K + 1;
   reserve(d_list_, 2 * rows_bytes + 256);
@@ -356,7 +361,8 @@ void Engine::dev_two_level(View& v, int K, const TcLayout& lay, bool first_try) 
   launches_ += 4;
   check(cudaEventRecord(ev_[6], stream_), "event");
   check(dev::estep_tc128_list(stream_, sms_, (const float*)v.X, v.N, v.gid, K, d_blob, d_as, d_it2, d_chat, d_lw, lrow,
-                              d_koff, d_tot, d_itoff, items_cap, d_items_.p, q, v.ldq, d_err, d_nitems, skip),
+                              d_koff, d_tot, d_itoff, items_cap, d_items_.p, q, v.ldq, d_err, d_nitems, skip,
+                              dev::tc_dim(v.D, v.ldx)),
         "estep_tc128_list launch");
   launches_ += 2;
   check(cudaEventRecord(ev_[7], stream_), "event");
@@ -377,7 +383,8 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
   const size_t es = prec_ == kF32 ? 4 : 8;
   const int64_t Sz = full ? (int64_t)D * D : D;
   const int64_t nJK = (int64_t)J * K, nstat = nJK + (int64_t)K * D + K * Sz;
-  const bool tc = prec_ == kF32 && full && use_tc_ && dev::tc_supported(D, v.ldx);
+  const int tdim = dev::tc_dim(D, v.ldx);
+  const bool tc = prec_ == kF32 && full && use_tc_ && tdim != 0;
   double* it = (double*)d_iter_.p;
   unsigned* ctl = reinterpret_cast<unsigned*>((unsigned char*)d_iter_.p + kCtlOff);
   const unsigned* skipE = ctl + dev::kCtlSkipE;
@@ -473,7 +480,7 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
         two_done = true;
       } else {
         check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, a.blob, a.as, a.it2, a.chatf, a.lwf, d_act,
-                               (float*)v.q, v.ldq, it + dev::kItSumLogZ, d_err, skipE),
+                               (float*)v.q, v.ldq, it + dev::kItSumLogZ, d_err, skipE, tdim),
               "estep_tc128 launch");
         ++launches_;
       }
@@ -530,7 +537,7 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
       const float* df = reinterpret_cast<const float*>(base + lay.off_f);
       const uint8_t* d_act = sparse_ ? (const uint8_t*)d_act_.p : nullptr;
       check(dev::estep_tc128(stream_, sms_, (const float*)v.X, v.N, v.gid, K, base, df, df + K, df + 2 * (size_t)K,
-                             df + 3 * (size_t)K, d_act, (float*)v.q, v.ldq, it + dev::kItSumLogZ, d_err, skipE),
+                             df + 3 * (size_t)K, d_act, (float*)v.q, v.ldq, it + dev::kItSumLogZ, d_err, skipE, tdim),
             "estep_tc128 launch");
       ++launches_;
       check(cudaEventRecord(ev_[3], stream_), "event");
@@ -552,7 +559,7 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
       if (cudaEventElapsedTime(&ms, ev_[6], ev_[7]) == cudaSuccess) estep_detail_[2] = ms;
       if (cudaEventElapsedTime(&ms, ev_[7], ev_[8]) == cudaSuccess) estep_detail_[3] = ms;
       cudaGetLastError();
-      if (tc_stage_ == 0 && v.J == 1 && !sparse_ && rec[dev::kItPairs] > 0) {
+      if (tc_stage_ == 0 && !sparse_ && rec[dev::kItPairs] > 0) {
         list_valid_ = true;
         list_q_ = v.q;
         list_K_ = K;

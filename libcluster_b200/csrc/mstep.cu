@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(kNT) mstep_cluster_kernel(MStepArgs a, int wor
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
           const int d = d0 + e;
-          const float v = d <= i ? (float)((sqn * A[(size_t)i * lda + d]) * bscale) : 0.f;
+          const float v = (d <= i && i < D) ? (float)((sqn * A[(size_t)i * lda + d]) * bscale) : 0.f;
           hi[e] = __float2half_rn(v);
           lo[e] = __float2half_rn(v - __half2float(hi[e]));
         }
@@ -268,10 +268,11 @@ __global__ void __launch_bounds__(kNT) mstep_cluster_kernel(MStepArgs a, int wor
         *reinterpret_cast<uint4*>(out + base_lo + off) = *reinterpret_cast<const uint4*>(lo);
       }
       float* mh_out = reinterpret_cast<float*>(out + kOffMean);
-      for (int d = tid; d < 128; d += kNT) {
-        const float hi = (float)rel[d];
+      for (int d = tid; d < 128; d += kNT) {  // the blob keeps its 128-dimensional layout for D = 64 (zeros above)
+        const double rd = d < D ? rel[d] : 0.0;
+        const float hi = (float)rd;
         mh_out[d] = hi;
-        mh_out[128 + d] = (float)(-(rel[d] - (double)hi) * s_scale);
+        mh_out[128 + d] = (float)(-(rd - (double)hi) * s_scale);
       }
       if (tid == 0) {
         a.as[k] = (float)s_scale;
@@ -544,7 +545,7 @@ __global__ void __launch_bounds__(kNT) mstep_finish_kernel(MStepArgs a) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) hs[e] = __float2half_rn(0.f);
       if (k < K && ok) {
-        double rem = -a.vaug[(size_t)k * D + i] / p2;
+        double rem = i < D ? -a.vaug[(size_t)k * D + i] / p2 : 0.0;
         for (int slot = 0; slot < 3; ++slot) {
           hs[slot] = __float2half_rn((float)rem);
           rem -= (double)__half2float(hs[slot]);

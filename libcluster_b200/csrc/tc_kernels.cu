@@ -30,6 +30,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 #include "tc_kernels.cuh"
@@ -46,7 +47,8 @@ namespace dev {
 
 namespace {
 
-constexpr int kD = 128;
+constexpr int kD = 128;  // widest row of the tier (the kernels are templated on DIM = 128 or 64)
+[[maybe_unused]] constexpr int kDUnused = kD;
 constexpr int kTM = 128;
 constexpr uint32_t kAPart = kTM * 128;            // one fp16 [128 x 64] swizzled block: 16384
 constexpr uint32_t kBBlob = kTcBlobBytes;         // B: kb0 hi(16K) lo(16K) kb1 hi(8K) lo(8K) | mhi (512) | -s*mlo (512)
@@ -195,6 +197,21 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -250,7 +267,11 @@ __device__ __forceinline__ ListItem list_item(int64_t it, int K, const int32_t* 
 // kList == true : the work items are 128-entry chunks of per-cluster row lists (lrow; item -> cluster through
 //                 itoff); the kernel writes the exact logit of every (row, cluster) pair into q[row][cluster]
 //                 and leaves the soft-max to estep_finalize_kernel.
-template <bool kList>
+// DIM == 64: the same kernel on 64-dimensional rows.  The operand blob keeps its 128-dimensional layout with
+// R_k in the upper-left 64 x 64 corner and zeros elsewhere, so K block 1 (input dimensions 64..127) contributes
+// nothing and is skipped: no builders for it, no MMAs, N = 64 - 16c output columns for chunk c, 64 accumulator
+// columns in the epilogue, and only the 17 KB of the blob that are read travel to shared memory.
+template <bool kList, int DIM>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __restrict__ gid, int K,
                    const uint8_t* __restrict__ blob, const float* __restrict__ ascale,
@@ -281,7 +302,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(BB_FULL0 + i), 1);
-      mbar_init(bar(BB_EMPTY0 + i), 9);  // MMA commit + 8 builder warps
+      mbar_init(bar(BB_EMPTY0 + i), DIM == 64 ? 5 : 9);  // MMA commit + the builder warps (4 per K block)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(bar(BA_FULL00 + i), 4);  // 4 lane quadrants
@@ -324,8 +345,17 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         for (int k = k0; k < k1; ++k, ++cnt) {
           const uint32_t st = cnt % NS, ph = (cnt / NS) & 1;
           mbar_wait(bar(BB_EMPTY0 + st), ph ^ 1, err);
-          mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
-          bulk_g2s(sB + st * kBBlob, blob + (size_t)k * kBBlob, kBBlob, bar(BB_FULL0 + st));
+          const uint8_t* src = blob + (size_t)k * kBBlob;
+          if constexpr (DIM == 128) {
+            mbar_expect_tx(bar(BB_FULL0 + st), kBBlob);
+            bulk_g2s(sB + st * kBBlob, src, kBBlob, bar(BB_FULL0 + st));
+          } else {
+            // rows 0..63 of K block 0 (hi, lo) and the mean vectors
+            mbar_expect_tx(bar(BB_FULL0 + st), 8192u + 8192u + 1024u);
+            bulk_g2s(sB + st * kBBlob, src, 8192u, bar(BB_FULL0 + st));
+            bulk_g2s(sB + st * kBBlob + kAPart, src + kAPart, 8192u, bar(BB_FULL0 + st));
+            bulk_g2s(sB + st * kBBlob + kOffMean, src + kOffMean, 1024u, bar(BB_FULL0 + st));
+          }
         }
       }
     }
@@ -354,28 +384,56 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
           const uint32_t sBk = sB + bs * kBBlob;
           const uint32_t a_hi0 = tmem_base + 256 + st * 128, a_lo0 = a_hi0 + 64;
           const uint32_t d0 = tmem_base + st * 128;
+          // Order of the 24 accumulating MMAs: the tensor core truncates when it adds into the fp32 accumulator, a
+          // bias of about half an ulp of the running sum per addition that shrinks |y| systematically (and, unlike
+          // rounding noise, pushes q the same way in every VB iteration: 1.7e-5 .. 3e-5 on q after three iterations
+          // of a soft 64-cluster fit with the products interleaved chunk by chunk, against 3e-6 for IEEE fp32,
+          // profiles/diag_soft_r02.log).  The cross products hi*lo and lo*hi are 2^-11 of the result: they go first,
+          // while the accumulator is still small and their truncations cost nothing; the eight hi*hi products
+          // follow, so only eight additions happen at full magnitude.
+          auto chunk_args = [&](int kb, int c4, uint32_t& dcol, uint32_t& acol, uint64_t& off, uint32_t& id) {
+            const uint32_t c = 4 * kb + c4, nc = DIM - 16 * c;
+            // first needed row of the stored block and the 16 fp16 along K inside the 128-byte row
+            off = (uint64_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
+            id = umma_idesc(nc);
+            dcol = d0 + 16 * c;
+            acol = 8 * c;
+          };
+          uint64_t dbh[2], dbl[2];
 #pragma unroll
-          for (int kb = 0; kb < 2; ++kb) {
+          for (int kb = 0; kb < DIM / 64; ++kb) {
             mbar_wait(bar(BA_FULL00 + 2 * st + kb), ph, err);
             tc_fence_after();
             const uint32_t b_hi = sBk + (kb == 0 ? 0u : 2 * kAPart);
             const uint32_t b_lo = b_hi + (kb == 0 ? kAPart : kAPart / 2);
-            const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
+            dbh[kb] = umma_desc(b_hi);
+            dbl[kb] = umma_desc(b_lo);
             if (elect_one()) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
-                const uint32_t c = 4 * kb + c4, nc = 128 - 16 * c;
-                // first needed row of the stored block and the 16 fp16 along K inside the 128-byte row
-                const uint64_t off = (uint64_t)(((16 * c - 64 * kb) * 128 + 32 * c4) >> 4);
-                const uint32_t id = umma_idesc(nc);
-                tc_mma_f16_ts(d0 + 16 * c, a_hi0 + 8 * c, dbh0 + off, id, (kb | c4) ? 1u : 0u);
-                tc_mma_f16_ts(d0 + 16 * c, a_hi0 + 8 * c, dbl0 + off, id, 1u);
-                tc_mma_f16_ts(d0 + 16 * c, a_lo0 + 8 * c, dbh0 + off, id, 1u);
+                uint32_t dcol, acol, id;
+                uint64_t off;
+                chunk_args(kb, c4, dcol, acol, off, id);
+                tc_mma_f16_ts(dcol, a_hi0 + acol, dbl[kb] + off, id, (kb | c4) ? 1u : 0u);
+                tc_mma_f16_ts(dcol, a_lo0 + acol, dbh[kb] + off, id, 1u);
               }
-              tc_commit(bar(BA_EMPTY00 + 2 * st + kb));
             }
             __syncwarp();
           }
+          if (elect_one()) {
+#pragma unroll
+            for (int kb = 0; kb < DIM / 64; ++kb) {
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint32_t dcol, acol, id;
+                uint64_t off;
+                chunk_args(kb, c4, dcol, acol, off, id);
+                tc_mma_f16_ts(dcol, a_hi0 + acol, dbh[kb] + off, id, 1u);
+              }
+              tc_commit(bar(BA_EMPTY00 + 2 * st + kb));
+            }
+          }
+          __syncwarp();
           if (elect_one()) {
             if (lastk) tc_commit(bar(BB_EMPTY0 + bs));
             tc_commit(bar(BT_FULL0 + st));
@@ -426,7 +484,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         tc_fence_after();
         float s = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) s += tmem_sumsq32(tmem_base + ((uint32_t)(ew * 32) << 16) + st * 128 + 32 * cc);
+        for (int cc = 0; cc < DIM / 32; ++cc) s += tmem_sumsq32(tmem_base + ((uint32_t)(ew * 32) << 16) + st * 128 + 32 * cc);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BT_EMPTY0 + st));
@@ -459,6 +517,8 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
       for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
       if (lane == 0) atomicAdd(Fz, fz);
     }
+  } else if (DIM == 64 && warp >= 12) {
+    // no K block 1 in 64 dimensions: these builder warps have nothing to do
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
     // ------------------------------------------------------ operand builders --
@@ -490,7 +550,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         const int rr = 2 * j + (lane >> 4);
         const int64_t nr = __shfl_sync(0xffffffffu, nrow, rr);
         const bool ok = nr < N;
-        const float* src = X + (ok ? nr : 0) * kD + 64 * kb + 4 * (lane & 15);
+        const float* src = X + (ok ? nr : 0) * DIM + 64 * kb + 4 * (lane & 15);
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(tbs + (uint32_t)rr * kTransRow + 16u * (uint32_t)(lane & 15)),
                      "l"(src), "r"(ok ? 16u : 0u)
                      : "memory");
@@ -552,7 +612,7 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
         it0 = it1;
         it1 = it2;
       } else if (n < N) {
-        const float4* src = reinterpret_cast<const float4*>(X + n * kD + 64 * kb);
+        const float4* src = reinterpret_cast<const float4*>(X + n * DIM + 64 * kb);
 #pragma unroll
         for (int j = 0; j < 16; ++j) x[j] = __ldg(src + j);
       } else {
@@ -631,34 +691,46 @@ estep_tc128_kernel(const float* __restrict__ X, int64_t N, const int32_t* __rest
 // already work on the next item (the first version launched one CTA per item and
 // spent more than half of its time in prologue, first-gather latency and the
 // flush, profiles/ncu_r01_sstat_v4_raw.csv).
-//   warp 0      list loader: (row, q) of the next 128 entries into shared memory
+//   warp 0      list loader: rows and sqrt(q) of the next 128 entries into shared memory
 //   warp 1      MMA issue
 //   warp 2      TMEM allocation
 //   warps 4-7   flush: tcgen05.ld of both accumulators, fp64 atomics
-//   warps 8-15  builders
+//   warps 8-23  builders: thread = (dimension, quarter of the tile's rows).  The first version had 8 builder warps
+//               with 64 rows per thread: two warps per scheduler could not cover the latency of the gathered loads
+//               (long-scoreboard stalls 2.0 per issue, issue slots 55 % busy, tensor pipe 30 %,
+//               profiles/ncu_r01_sstat_v6_raw.csv); 16 warps with 32 rows each double the loads in flight per
+//               scheduler, and the centring / weighting / hi-lo split runs on packed f32x2 instructions.
 // ===========================================================================
-constexpr int kScatterThreads = 512;
+constexpr int kScatterThreads = 768;
 constexpr uint32_t kSB_Stage = 65536; // per stage: K block 0 (hi 16K, lo 16K), K block 1 (hi, lo)
 constexpr uint32_t kSOffList = 2 * kSB_Stage;
-constexpr uint32_t kSOffPre = kSOffList + 2 * 128 * 8;        // item prefix per cluster: (kTcCoarseMaxK + 1) ints
+constexpr int kSListStages = 8;                               // list tiles the loader (and its L2 prefetch) runs ahead
+constexpr uint32_t kSOffPre = kSOffList + kSListStages * 1024;  // item prefix per cluster: (kTcCoarseMaxK + 1) ints
 constexpr uint32_t kSOffBar = kSOffPre + 4 * (kTcCoarseMaxK + 8);
-constexpr uint32_t kSSmemBytes = kSOffBar + 256 + 1024;
+constexpr uint32_t kSOffTri = kSOffBar + 256;                 // fp64 running sums of the current cluster, lower triangle
+constexpr uint32_t kSTriBytes = 128 * 129 / 2 * 8;            // 66048
+constexpr uint32_t kSSmemBytes = kSOffTri + kSTriBytes + 1024;
+static_assert(kSOffTri % 8 == 0 && kSSmemBytes <= 232448, "S pass shared memory");
 enum {
-  SL_FULL0 = 0, SL_EMPTY0 = 2, SAB_FULL00 = 4 /* [stage][h] */, SAB_EMPTY00 = 8, SACC_FULL = 12, SACC_EMPTY = 13,
-  SB_COUNT = 14
+  SL_FULL0 = 0, SL_EMPTY0 = 8, SAB_FULL00 = 16 /* [stage][h] */, SAB_EMPTY00 = 20, SACC_FULL = 24, SACC_EMPTY = 25,
+  SB_COUNT = 26
 };
+static_assert(8 * SB_COUNT + 8 <= 256 && kSListStages == 8, "barrier block of the S pass");
 
 struct ScatterItem {
   int k, ntile;
   long long l0, l1, base;
 };
 
+// DIM == 64: dimensions 64..127 do not exist: their builder and flush warps idle, the MMAs run with N = 64 (the A
+// rows 64..127 in TMEM are never written and the accumulator rows they produce are never read).
+template <int DIM>
 __global__ void __launch_bounds__(kScatterThreads, 1)
 sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow, const float* __restrict__ lq,
                    const long long* __restrict__ koff, const long long* __restrict__ kcnt, int K,
                    const float* __restrict__ cen, float scale, int chunk_rows, double* __restrict__ xs,
                    double* __restrict__ S, unsigned* __restrict__ err, const float* __restrict__ scale_dev,
-                   const unsigned* __restrict__ skip) {
+                   const unsigned* __restrict__ skip, int pf) {
   extern __shared__ unsigned char smem_dyn[];
   if (skip != nullptr && *skip != 0u) return;
   if (scale_dev != nullptr) scale = *scale_dev;  // chosen by the device M step from the centres it produced
@@ -671,16 +743,16 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSListStages; ++i) {
       mbar_init(bar(SL_FULL0 + i), 1);
-      mbar_init(bar(SL_EMPTY0 + i), 8);
+      mbar_init(bar(SL_EMPTY0 + i), DIM / 8);   // builder warps: 4 quarters of the rows x DIM / 32 lane quadrants
     }
     for (int i = 0; i < 4; ++i) {
-      mbar_init(bar(SAB_FULL00 + i), 4);
+      mbar_init(bar(SAB_FULL00 + i), DIM / 16);
       mbar_init(bar(SAB_EMPTY00 + i), 1);
     }
     mbar_init(bar(SACC_FULL), 1);
-    mbar_init(bar(SACC_EMPTY), 4);
+    mbar_init(bar(SACC_EMPTY), DIM / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     int acc = 0;
     for (int k = 0; k < K; ++k) {
@@ -701,6 +773,12 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const int nitems = pre[K];
+  // A contiguous range of items per CTA: the items are ordered by cluster, so a CTA meets two or three clusters in a
+  // pass and can keep the running sums of the current one on chip (the first version strided the items over the CTAs
+  // and added every 512-row accumulator to the global statistics: 16 K fp64 atomics per item, 1.6 G per pass at
+  // N = 50 M -- the pass ran at the L2's atomic rate, 145 G/s, whatever the builders did).
+  const int it_beg = (int)(((long long)nitems * blockIdx.x) / gridDim.x);
+  const int it_end = (int)(((long long)nitems * (blockIdx.x + 1)) / gridDim.x);
   // item -> (cluster, list range): the last cluster whose prefix is <= it
   auto item_of = [&](int it) {
     int lo = 0, hi = K - 1;
@@ -720,34 +798,65 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
   };
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    // Register budget: the CTA owns 768 x 80 registers and setmaxnreg can only move registers inside that pool
+    // (24 warps x 80 = 1920 per lane): control 4 x 48, flush 4 x 104, builders 16 x 80 = 1888.
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
     if (warp == 0) {
       // ---- list loader: (row, q) of the next 128 list entries into shared memory ----
       uint32_t tc = 0;
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+      for (int it = it_beg; it < it_end; ++it) {
         const ScatterItem w = item_of(it);
         for (int t = 0; t < w.ntile; ++t, ++tc) {
-          const uint32_t st = tc & 1;
-          mbar_wait(bar(SL_EMPTY0 + st), ((tc >> 1) & 1) ^ 1, err);
-          int2* dst = reinterpret_cast<int2*>(sgen + kSOffList + st * 1024);
+          // The loader runs up to kSListStages tiles ahead of the builders and asks the L2 for the rows of every
+          // tile it lists: the builders' gathers, issued several tile times later, find them there.  (With a
+          // two-deep list ring and no prefetch the pass was bound by the latency chain list load -> gather from
+          // DRAM -> build: 4.5 us per tile against 1 us of tensor work, whatever the number of builder warps and
+          // however few atomics the flush issued.)
+          const uint32_t st = tc & (kSListStages - 1);
+          mbar_wait_patient(bar(SL_EMPTY0 + st), ((tc / kSListStages) & 1) ^ 1, err);
+          // [128 rows (int32)][128 sqrt(q) (fp32)]; entries past the end of the list read row 0 with weight 0
+          int* drow = reinterpret_cast<int*>(sgen + kSOffList + st * 1024);
+          float* dw = reinterpret_cast<float*>(drow + 128);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const long long l = w.l0 + (long long)t * 128 + e * 32 + lane;
-            int2 v = make_int2(-1, 0);
+            int row = 0;
+            float wq = 0.f;
             if (l < w.l1) {
-              v.x = lrow[w.base + l];
-              v.y = __float_as_int(sqrtf(lq[w.base + l]));  // the builders work with sqrt(q), see below
+              row = lrow[w.base + l];
+              wq = sqrtf(lq[w.base + l]);  // the builders work with sqrt(q), see below
+              if (pf == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(X + (size_t)row * DIM), "n"(DIM * 4) : "memory");
             }
-            dst[e * 32 + lane] = v;
+            drow[e * 32 + lane] = row;
+            dw[e * 32 + lane] = wq;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(SL_FULL0 + st));
         }
       }
+    } else if (warp == 3 && pf == 1) {
+      // ---- L2 prefetch (optional): the rows of the tile the loader has just listed, all 128-byte lines of a row
+      // back to back, so that the builders' gathers -- one 128-byte piece of a row per warp instruction, the four
+      // pieces from four different warps at four different times -- find the row in L2 ----
+      uint32_t tc = 0;
+      for (int it = it_beg; it < it_end; ++it) {
+        const ScatterItem w = item_of(it);
+        for (int t = 0; t < w.ntile; ++t, ++tc) {
+          const uint32_t st = tc & (kSListStages - 1);
+          mbar_wait_patient(bar(SL_FULL0 + st), (tc / kSListStages) & 1, err);
+          const int* rows = reinterpret_cast<const int*>(sgen + kSOffList + st * 1024);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const char* p = reinterpret_cast<const char*>(X + (size_t)rows[e * 32 + lane] * DIM);
+#pragma unroll
+            for (int b = 0; b < DIM * 4; b += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + b) : "memory");
+          }
+        }
+      }
     } else if (warp == 1) {
       // ---- MMA issuer ----
       uint32_t tc = 0, ic = 0;
-      for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++ic) {
+      for (int it = it_beg; it < it_end; ++it, ++ic) {
         const ScatterItem w = item_of(it);
         // the flush warps must have read the previous item's accumulators
         mbar_wait(bar(SACC_EMPTY), (ic & 1) ^ 1, err);
@@ -762,7 +871,7 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
             tc_fence_after();
             const uint32_t b_hi = sbase + st * kSB_Stage + h * 32768, b_lo = b_hi + 16384;
             const uint64_t dbh0 = umma_desc(b_hi), dbl0 = umma_desc(b_lo);
-            const uint32_t id = umma_idesc(128);
+            const uint32_t id = umma_idesc(DIM);
             if (elect_one()) {
               // The hi*hi products and the 2^-11 smaller cross terms go to separate accumulators: the tensor core
               // truncates when it adds into the fp32 accumulator, and the bias of a chain of n additions (~ n/2 ulp
@@ -786,123 +895,170 @@ sstat_tc128_kernel(const float* __restrict__ X, const int32_t* __restrict__ lrow
       }
     }
   } else if (warp < 8) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-    // ---- flush: accumulators -> fp64 global statistics (S is symmetric: lane i writes column i) ----
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    // ---- flush: accumulators -> fp64 running sums of the current cluster in shared memory (lower triangle: lane i
+    // owns row i, columns j <= i); the sums go to the global statistics, both triangles, when the CTA's items move on
+    // to another cluster ----
     const int quad = warp & 3;
     const int i = 32 * quad + lane;
     const double inv_s = 1.0 / (double)scale, inv_s2 = inv_s * inv_s;
+    double* tri = reinterpret_cast<double*>(sgen + kSOffTri) + (size_t)i * (i + 1) / 2;
+    const bool mine = i < DIM;
+    if (mine)
+      for (int j = 0; j <= i; ++j) tri[j] = 0.0;
+    auto dump = [&](int k) {
+      double* Sk = S + (size_t)k * DIM * DIM;
+      for (int j = 0; j <= i; ++j) {
+        const double v = tri[j] * inv_s2;
+        tri[j] = 0.0;
+        if (v != 0.0) {
+          atomicAdd(&Sk[(size_t)i * DIM + j], v);
+          if (j != i) atomicAdd(&Sk[(size_t)j * DIM + i], v);
+        }
+      }
+    };
     uint32_t ic = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, ++ic) {
+    int kcur = -1;
+    for (int it = it_beg; it < (mine ? it_end : it_beg); ++it, ++ic) {
       const ScatterItem w = item_of(it);
-      double* Sk = S + (size_t)w.k * kD * kD;
+      if (w.k != kcur) {
+        if (kcur >= 0) dump(kcur);
+        kcur = w.k;
+      }
       mbar_wait(bar(SACC_FULL), ic & 1, err);
       tc_fence_after();
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        uint32_t r[32], r2[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 32 * cc)
-            : "memory");
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7]),
-              "=r"(r2[8]), "=r"(r2[9]), "=r"(r2[10]), "=r"(r2[11]), "=r"(r2[12]), "=r"(r2[13]), "=r"(r2[14]), "=r"(r2[15]),
-              "=r"(r2[16]), "=r"(r2[17]), "=r"(r2[18]), "=r"(r2[19]), "=r"(r2[20]), "=r"(r2[21]), "=r"(r2[22]), "=r"(r2[23]),
-              "=r"(r2[24]), "=r"(r2[25]), "=r"(r2[26]), "=r"(r2[27]), "=r"(r2[28]), "=r"(r2[29]), "=r"(r2[30]), "=r"(r2[31])
-            : "r"(tmem_base + ((uint32_t)(32 * quad) << 16) + 128 + 32 * cc)
-            : "memory");
+      for (int cc = 0; cc <= 2 * quad + 1; ++cc) {  // 16-column blocks that hold a j <= i for some lane of this warp
+        uint32_t r[16], r2[16];
+        tmem_ld16(tmem_base + ((uint32_t)(32 * quad) << 16) + 16 * cc, r);
+        tmem_ld16(tmem_base + ((uint32_t)(32 * quad) << 16) + 128 + 16 * cc, r2);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (cc == 3) {
-          // everything has been read: the next item may overwrite the accumulators while the last adds go out
+        if (cc == 2 * quad + 1) {
+          // everything this warp needs has been read: the next item may overwrite the accumulators
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar(SACC_EMPTY));
         }
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const double v = ((double)__uint_as_float(r[jj]) + (double)__uint_as_float(r2[jj])) * inv_s2;
-          if (v != 0.0) atomicAdd(&Sk[(size_t)(32 * cc + jj) * kD + i], v);
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = 16 * cc + jj;
+          if (j <= i) tri[j] += (double)__uint_as_float(r[jj]) + (double)__uint_as_float(r2[jj]);
         }
       }
     }
+    if (kcur >= 0) dump(kcur);
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    // ---- builders: thread = dimension i (TMEM lane, B row), half h of the tile's rows ----
-    const int quad = warp & 3, h = (warp - 8) >> 2;
+    // ---- builders: thread = dimension i (TMEM lane, B row), rows [32 hg, 32 hg + 32) of the tile ----
+    // The gathers run one half step ahead of the arithmetic: the 32 rows of a thread are two batches of 16
+    // (8 float2 registers each); as soon as a batch has been consumed its registers are reloaded with the same
+    // batch of the NEXT tile of this CTA (the list ring is kSListStages deep, so its rows are known), so the loads
+    // of a batch are in flight during the arithmetic of the other batch, the operand stores and the barrier
+    // hand-offs.  (Loading all 32 rows and then using them exposed the whole gather latency once per tile: the
+    // first use of a loaded value and the load issue queue held half of all stall samples,
+    // profiles/ncu_r02_sstat_v1_*.)
+    const int quad = warp & 3, hg = (warp - 8) >> 2, h = hg >> 1, g = hg & 1;
     const int i = 32 * quad + lane;
     const double inv_s = 1.0 / (double)scale;
+    const float2 sc2 = make_float2(scale, scale);
+    const bool active = 32 * quad < DIM;
+    // tiles of this CTA in order: tile counter tc -> list stage; the items only matter for the centre and the sums
+    float2 a[16];
+    auto load_batch = [&](uint32_t tcn, int b) {
+      const uint32_t lst = tcn & (kSListStages - 1);
+      const int4* rows4 = reinterpret_cast<const int4*>(sgen + kSOffList + lst * 1024) + 8 * hg + 4 * b;
+#pragma unroll
+      for (int r4 = 0; r4 < 4; ++r4) {
+        const int4 rr = rows4[r4];
+        a[8 * b + 2 * r4].x = __ldg(X + (size_t)rr.x * DIM + i);
+        a[8 * b + 2 * r4].y = __ldg(X + (size_t)rr.y * DIM + i);
+        a[8 * b + 2 * r4 + 1].x = __ldg(X + (size_t)rr.z * DIM + i);
+        a[8 * b + 2 * r4 + 1].y = __ldg(X + (size_t)rr.w * DIM + i);
+      }
+    };
+    // total tiles of this CTA (for the look-ahead)
+    uint32_t ntiles_cta = 0;
+    if (active)
+      for (int it = it_beg; it < it_end; ++it) ntiles_cta += (uint32_t)item_of(it).ntile;
     uint32_t tc = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    if (active && ntiles_cta > 0) {
+      mbar_wait(bar(SL_FULL0 + 0), 0, err);
+      load_batch(0, 0);
+      load_batch(0, 1);
+    }
+    for (int it = it_beg; it < (active ? it_end : it_beg); ++it) {
       const ScatterItem w = item_of(it);
-      const float ncs = -cen[(size_t)w.k * kD + i] * scale;
+      const float ncs = -cen[(size_t)w.k * DIM + i] * scale;
+      const float2 ncs2 = make_float2(ncs, ncs);
       double xs64 = 0.0;
       for (int t = 0; t < w.ntile; ++t, ++tc) {
         const uint32_t st = tc & 1;
         const uint32_t ph = (tc >> 1) & 1;
-        mbar_wait(bar(SL_FULL0 + st), ph, err);
-        const int2* lst = reinterpret_cast<const int2*>(sgen + kSOffList + st * 1024) + 64 * h;
-        float a[64];
-#pragma unroll
-        for (int r = 0; r < 64; ++r) {
-          const int row = lst[r].x;
-          a[r] = row >= 0 ? __ldg(X + (size_t)row * kD + i) : 0.f;
-        }
-        float xs32 = 0.f;
+        const uint32_t lst = tc & (kSListStages - 1);
+        const bool more = tc + 1 < ntiles_cta;
+        const float2* wq2 = reinterpret_cast<const float2*>(sgen + kSOffList + lst * 1024 + 512) + 16 * hg;
+        unsigned long long xs2 = 0ull;  // packed pair of fp32 partial sums of q (x - c) s
         mbar_wait(bar(SAB_EMPTY00 + 2 * st + h), ph ^ 1, err);
         tc_fence_after();
-        const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 256 + st * 128 + 32 * h;
+        const uint32_t tA = tmem_base + ((uint32_t)(32 * quad) << 16) + 256 + st * 128 + 32 * h + 16 * g;
         const uint32_t bRow = sbase + st * kSB_Stage + h * 32768 + (uint32_t)i * 128u;
+        uint32_t ah[8], al[8];   // eight packed columns (16 rows) at a time: stored to TMEM after every second chunk
 #pragma unroll
-        for (int g = 0; g < 2; ++g) {  // 32 rows per group: 16 packed columns of A, 4 chunks of B
-          uint32_t ah[16], al[16];
+        for (int c = 0; c < 4; ++c) {
+          uint32_t bh[4], bl[4];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            uint32_t bh[4], bl[4];
-#pragma unroll
-            for (int p = 0; p < 4; ++p) {
-              // S_k = sum_r (w a)(w a)^T with w = sqrt(q): both MMA operands are the same numbers (A in TMEM, B in
-              // shared memory), so one scaling and one fp16 hi/lo split serve both
-              const int r = 32 * g + 8 * c + 2 * p;
-              const int2 e0 = lst[r], e1 = lst[r + 1];
-              const float w0 = __int_as_float(e0.y), w1 = __int_as_float(e1.y);
-              const float a0 = e0.x >= 0 ? w0 * fmaf(a[r], scale, ncs) : 0.f;
-              const float a1 = e1.x >= 0 ? w1 * fmaf(a[r + 1], scale, ncs) : 0.f;
-              const uint32_t hh = pack_f16x2_sat(a0, a1);
-              const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
-              const uint32_t ll = pack_f16x2_sat(a0 - hf.x, a1 - hf.y);
-              ah[4 * c + p] = hh;
-              al[4 * c + p] = ll;
-              bh[p] = hh;
-              bl[p] = ll;
-              xs32 = fmaf(w0, a0, fmaf(w1, a1, xs32));
-            }
-            const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 16384u), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
+          for (int p = 0; p < 4; ++p) {
+            // S_k = sum_r (w a)(w a)^T with w = sqrt(q): both MMA operands are the same numbers (A in TMEM, B in
+            // shared memory), so one scaling and one fp16 hi/lo split serve both.  Two rows per instruction.
+            const int pr = 4 * c + p;
+            const float2 wv = wq2[pr];
+            unsigned long long X2 = *reinterpret_cast<const unsigned long long*>(&a[pr]);
+            const unsigned long long S2 = *reinterpret_cast<const unsigned long long*>(&sc2);
+            const unsigned long long N2 = *reinterpret_cast<const unsigned long long*>(&ncs2);
+            const unsigned long long W2 = *reinterpret_cast<const unsigned long long*>(&wv);
+            unsigned long long T2, V2, D2;
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(T2) : "l"(X2), "l"(S2), "l"(N2));
+            asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(V2) : "l"(T2), "l"(W2));
+            const float2 v = *reinterpret_cast<const float2*>(&V2);
+            const uint32_t hh = pack_f16x2_sat(v.x, v.y);
+            const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hh));
+            const unsigned long long H2 = *reinterpret_cast<const unsigned long long*>(&hf);
+            asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(D2) : "l"(V2), "l"(H2));
+            const float2 dl = *reinterpret_cast<const float2*>(&D2);
+            const uint32_t ll = pack_f16x2_sat(dl.x, dl.y);
+            ah[pr & 7] = hh;
+            al[pr & 7] = ll;
+            bh[p] = hh;
+            bl[p] = ll;
+            asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(xs2) : "l"(V2), "l"(W2));
           }
-          tmem_st16(tA + 16 * g, ah);
-          tmem_st16(tA + 64 + 16 * g, al);
+          const uint32_t off = bRow + ((((uint32_t)(4 * g + c)) ^ ((uint32_t)i & 7u)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off), "r"(bh[0]), "r"(bh[1]), "r"(bh[2]), "r"(bh[3]) : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(off + 16384u), "r"(bl[0]), "r"(bl[1]), "r"(bl[2]), "r"(bl[3]) : "memory");
+          if (c & 1) {
+            tmem_st8(tA + 4 * (c - 1), ah);
+            tmem_st8(tA + 64 + 4 * (c - 1), al);
+          }
+          if (c == 1 && more) {
+            // batch 0 is consumed: reload it with the next tile's rows (its list stage must have been filled)
+            mbar_wait(bar(SL_FULL0 + ((tc + 1) & (kSListStages - 1))), ((tc + 1) / kSListStages) & 1, err);
+            load_batch(tc + 1, 0);
+          }
+          if (c == 3 && more) load_batch(tc + 1, 1);
         }
-        xs64 += (double)xs32;
+        {
+          const float2 xp = *reinterpret_cast<const float2*>(&xs2);
+          xs64 += (double)(xp.x + xp.y);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(bar(SAB_FULL00 + 2 * st + h));
-          mbar_arrive(bar(SL_EMPTY0 + st));
+          mbar_arrive(bar(SL_EMPTY0 + lst));
         }
       }
-      if (xs64 != 0.0) atomicAdd(&xs[(size_t)w.k * kD + i], xs64 * inv_s);
+      if (xs64 != 0.0) atomicAdd(&xs[(size_t)w.k * DIM + i], xs64 * inv_s);
     }
   }
 
@@ -959,7 +1115,7 @@ constexpr uint32_t kCOffBar = kCOffLb + 2 * 2 * kCRows * 4;    // 215040
 constexpr uint32_t kCSmemBytes = kCOffBar + 512 + 1024;
 constexpr uint32_t kCAcol = 72;                                // TMEM columns of one A slot
 enum {
-  CB_FULL0 = 0, CB_EMPTY0 = 3, CG_FULL0 = 6, CG_EMPTY0 = 8, CA_READY0 = 10, CA_FREE0 = 13, CT_FULL0 = 16, CT_EMPTY0 = 18,
+  CB_FULL0 = 0, CB_EMPTY0 = 3, CG_FULL0 = 6, CG_EMPTY0 = 8, CA_READY0 = 10, CA_FREE0 = 13, CT_FULL0 = 16 /* 4 */,
   CL_FULL0 = 20, CL_FREE0 = 22, C_COUNT = 24
 };
 
@@ -981,16 +1137,13 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
-               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-// sum of squares of 128 fp32 register values: eight independent chains of packed FMAs, packed adds to fold them
-__device__ __forceinline__ float sumsq128(const uint32_t* r) {
+// sum of squares of NV (128 or 64) fp32 register values: eight independent chains of packed FMAs, packed adds to
+// fold them
+template <int NV>
+__device__ __forceinline__ float sumsq_regs(const uint32_t* r) {
   unsigned long long acc[8] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
 #pragma unroll
-  for (int i = 0; i < 128; i += 16) {
+  for (int i = 0; i < NV; i += 16) {
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       unsigned long long p;
@@ -1018,7 +1171,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // issuer left the tensor pipe 57 % idle, two issuers 33 % (profiles/ncu_r01_coarse_v2_raw.csv, ..._v3_raw.csv).
 // Shared-memory addresses derive from the kernel parameter sbase_hint and the loop counters only (TMEM base = 0: the
 // CTA owns all 512 columns), which keeps the loop on the uniform datapath.
-template <uint32_t S>
+template <uint32_t S, int DIM>
 __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ngroups, unsigned* err) {
   constexpr uint32_t a0 = 256u + kCAcol * S;
   const uint32_t barb = sb + kCOffBar;
@@ -1036,7 +1189,10 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
       mbar_wait(barb + 8u * (CB_FULL0 + bs), bph, err);
       const uint32_t lo0 = blo_base + bs * (kCBStage >> 4), lo1 = lo0 + (16384u >> 4);
       const uint32_t log_ = glo_base + as * (kTcAugBlockBytes >> 4) + 2u * (uint32_t)(k & 3);
-      const uint32_t acc = ic & 1u;
+      // accumulators: two of 128 columns, or -- 64 dimensions -- four of 64 columns, so that twice as many items are
+      // in flight between issue and drain (at 112 tensor clocks per item the hand-off latency is what counts)
+      constexpr uint32_t NACC = DIM == 64 ? 4u : 2u, LGA = DIM == 64 ? 2u : 1u, ACCW = DIM == 64 ? 64u : 128u;
+      const uint32_t acc = ic & (NACC - 1u);
       const bool last = k == K - 1, aug_done = (k & 3) == 3 || last;
       if (elect_one()) {
         // One asm block: wait until the epilogue has drained the accumulator -- the previous ic >> 1 items that used
@@ -1048,6 +1204,7 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
         //   N = 128 - 16c), and the commit.
         // Instruction descriptors: D = f32, A = B = f16, K-major, M = 128, N as above.  The spin is bounded: a
         // protocol bug traps instead of hanging the device.
+        if constexpr (DIM == 128) {
         asm volatile(
             "{\n\t"
             ".reg .pred p, q, r;\n\t"
@@ -1091,9 +1248,47 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
             "}"
-            ::"r"(barb + 8u * C_COUNT + 16u + 4u * acc), "r"(4u * (ic >> 1)), "r"(128u * acc), "r"(a0), "r"(lo0), "r"(lo1),
+            ::"r"(barb + 8u * C_COUNT + 16u + 4u * acc), "r"(4u * (ic >> LGA)), "r"(ACCW * acc), "r"(a0), "r"(lo0), "r"(lo1),
               "r"(log_), "r"(kDescHi), "r"(barb + 8u * (CT_FULL0 + acc)), "r"(barb + 8u * (CB_EMPTY0 + bs))
             : "memory");
+        } else {
+          // 64 dimensions: the aug chunk and the four triangular chunks of K block 0, N = 64 - 16c
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p, q, r;\n\t"
+            ".reg .b64 bd;\n\t"
+            ".reg .b32 t, c;\n\t"
+            "setp.ne.b32 p, 1, 0;\n\t"
+            "mov.u32 c, 0;\n\t"
+            "CW6_WAIT_%=:\n\t"
+            "add.u32 c, c, 1;\n\t"
+            "setp.gt.u32 r, c, 67108864;\n\t"
+            "@r trap;\n\t"
+            "ld.acquire.cta.shared.u32 t, [%0];\n\t"
+            "sub.u32 t, t, %1;\n\t"
+            "setp.lt.s32 q, t, 0;\n\t"
+            "@q bra CW6_WAIT_%=;\n\t"
+            "tcgen05.fence::after_thread_sync;\n\t"
+            "mov.b64 bd, {%6, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3+64], bd, 0x8100010, !p;\n\t"
+            "mov.b64 bd, {%4, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2], [%3], bd, 0x8100010, p;\n\t"
+            "add.u32 t, %4, 0x82;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+16], [%3+8], bd, 0x80c0010, p;\n\t"
+            "add.u32 t, %4, 0x104;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+32], [%3+16], bd, 0x8080010, p;\n\t"
+            "add.u32 t, %4, 0x186;\n\t"
+            "mov.b64 bd, {t, %7};\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%2+48], [%3+24], bd, 0x8040010, p;\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%8];\n\t"
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%9];\n\t"
+            "}"
+            ::"r"(barb + 8u * C_COUNT + 16u + 4u * acc), "r"(4u * (ic >> LGA)), "r"(ACCW * acc), "r"(a0), "r"(lo0), "r"(lo1),
+              "r"(log_), "r"(kDescHi), "r"(barb + 8u * (CT_FULL0 + acc)), "r"(barb + 8u * (CB_EMPTY0 + bs))
+            : "memory");
+        }
         if (aug_done) tc_commit(barb + 8u * (CG_EMPTY0 + as));
         if (last) tc_commit(barb + 8u * (CA_FREE0 + S));
       }
@@ -1106,6 +1301,7 @@ __device__ __forceinline__ void coarse_mma_issuer(uint32_t sb, int K, int64_t ng
   }
 }
 
+template <int DIM>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__ xnorm, int64_t N,
                           const int32_t* __restrict__ gid, int K, const uint8_t* __restrict__ blob,
@@ -1154,13 +1350,13 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       mbar_init(bar(CG_FULL0 + i), 1);
       mbar_init(bar(CG_EMPTY0 + i), 3);  // the three MMA issuers
       mbar_init(bar(CT_FULL0 + i), 1);
+      mbar_init(bar(CT_FULL0 + 2 + i), 1);  // accumulators 2 and 3 (64 dimensions)
       mbar_init(bar(CL_FULL0 + i), 8);   // 8 epilogue warps
       mbar_init(bar(CL_FREE0 + i), 4);   // 4 stager warps
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // drained-items counters of the two accumulators (4 arrivals per item), behind the TMEM slot
-    reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT + 16)[0] = 0u;
-    reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT + 16)[1] = 0u;
+    for (int i = 0; i < 4; ++i) reinterpret_cast<volatile uint32_t*>(sgen + kCOffBar + 8 * C_COUNT + 16)[i] = 0u;
   }
   for (int i = (int)tid; i < 4 * 256; i += kThreadsTc) {
     const int a = i >> 8, k = i & 255;
@@ -1202,16 +1398,21 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
           }
           const uint32_t bs = bcnt % kCStages, bph = (bcnt / kCStages) & 1;
           mbar_wait_patient(bar(CB_EMPTY0 + bs), bph ^ 1, err);
-          mbar_expect_tx(bar(CB_FULL0 + bs), kCBStage);
           const uint8_t* src = blob + (size_t)k * kBBlob;
-          bulk_g2s(sbase + bs * kCBStage, src, 16384u, bar(CB_FULL0 + bs));                  // hi, dims 0..63
-          bulk_g2s(sbase + bs * kCBStage + 16384u, src + 32768u, 8192u, bar(CB_FULL0 + bs));  // hi, dims 64..127
+          if constexpr (DIM == 128) {
+            mbar_expect_tx(bar(CB_FULL0 + bs), kCBStage);
+            bulk_g2s(sbase + bs * kCBStage, src, 16384u, bar(CB_FULL0 + bs));                  // hi, dims 0..63
+            bulk_g2s(sbase + bs * kCBStage + 16384u, src + 32768u, 8192u, bar(CB_FULL0 + bs));  // hi, dims 64..127
+          } else {
+            mbar_expect_tx(bar(CB_FULL0 + bs), 8192u);
+            bulk_g2s(sbase + bs * kCBStage, src, 8192u, bar(CB_FULL0 + bs));                   // hi, rows and dims 0..63
+          }
         }
       }
     }
-    if (warp == 1) coarse_mma_issuer<0>(sbase_hint, K, ngroups, err);
-    if (warp == 2) coarse_mma_issuer<1>(sbase_hint, K, ngroups, err);
-    if (warp == 3) coarse_mma_issuer<2>(sbase_hint, K, ngroups, err);
+    if (warp == 1) coarse_mma_issuer<0, DIM>(sbase_hint, K, ngroups, err);
+    if (warp == 2) coarse_mma_issuer<1, DIM>(sbase_hint, K, ngroups, err);
+    if (warp == 3) coarse_mma_issuer<2, DIM>(sbase_hint, K, ngroups, err);
   } else if (warp < 8) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
     // --------------------------------------------------------------- stagers --
@@ -1221,15 +1422,17 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
       for (int t = 0; t < kCT; ++t) {
         const int64_t n0 = gi * kCRows + (int64_t)t * kTM;
         unsigned char* dstT = sgen + kCOffStageA + (uint32_t)t * kCStageA;
+        // lanes per row: 16 (128 dimensions, 8 floats each) or 8 (64 dimensions)
+        constexpr int LPR = DIM / 8, RPW = 32 / LPR, NIT = kTM / (4 * RPW);
 #pragma unroll 1
-        for (int it0 = 0; it0 < 16; it0 += 4) {
+        for (int it0 = 0; it0 < NIT; it0 += 4) {
           float4 v[4][2];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
+            const int r = RPW * ((it0 + u) * 4 + sw) + lane / LPR;
             const int64_t n = n0 + r;
             if (n < N) {
-              const float4* src = reinterpret_cast<const float4*>(X + n * kD + 8 * (lane & 15));
+              const float4* src = reinterpret_cast<const float4*>(X + n * DIM + 8 * (lane % LPR));
               v[u][0] = __ldg(src);
               v[u][1] = __ldg(src + 1);
             } else {
@@ -1238,13 +1441,13 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            const int r = 2 * ((it0 + u) * 4 + sw) + (lane >> 4);
+            const int r = RPW * ((it0 + u) * 4 + sw) + lane / LPR;
             uint4 w;
             w.x = pack_f16x2_sat(v[u][0].x * sg, v[u][0].y * sg);
             w.y = pack_f16x2_sat(v[u][0].z * sg, v[u][0].w * sg);
             w.z = pack_f16x2_sat(v[u][1].x * sg, v[u][1].y * sg);
             w.w = pack_f16x2_sat(v[u][1].z * sg, v[u][1].w * sg);
-            *reinterpret_cast<uint4*>(dstT + r * 256 + (((lane & 15) ^ (r & 15)) << 4)) = w;
+            *reinterpret_cast<uint4*>(dstT + r * 256 + (((lane % LPR) ^ (r & 15)) << 4)) = w;
           }
         }
       }
@@ -1294,7 +1497,7 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
         const unsigned char* srcT = sgen + kCOffStageA + (uint32_t)s * kCStageA + row * 256;
         const uint32_t tA = tmem_base + ((uint32_t)(32 * sw) << 16) + 256u + kCAcol * (uint32_t)s;
 #pragma unroll
-        for (int h = 0; h < 4; ++h) {
+        for (int h = 0; h < DIM / 32; ++h) {
           uint32_t rr[16];
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
@@ -1336,8 +1539,8 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
     asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
     // -------------------------------------------------------------- epilogue --
     const int grp = (warp - 8) >> 2, quad = warp & 3;
-    const uint32_t tacc = tmem_base + ((uint32_t)(32 * quad) << 16) + 128u * (uint32_t)grp;
-    const uint32_t bfull = bar(CT_FULL0 + grp), drained = sBar + 8u * C_COUNT + 16u + 4u * (uint32_t)grp;
+    constexpr uint32_t NACC = DIM == 64 ? 4u : 2u, LGA = DIM == 64 ? 2u : 1u, ACCW = DIM == 64 ? 64u : 128u;
+    const uint32_t tacc0 = tmem_base + ((uint32_t)(32 * quad) << 16);
     const bool grouped = gid != nullptr;
     const bool special = grouped || act != nullptr;  // per-row weights or an active mask: the rare, slower tail
     const uint32_t spar_s = sbase + kCOffPar;
@@ -1367,8 +1570,12 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ch) : "r"(spar_s + 4u * (uint32_t)k + 3072u));
 #pragma unroll
         for (int s = 0; s < kCT; ++s, ++icnt) {
-          // the icnt-th item of this CTA lives in accumulator icnt & 1 (see the MMA issuers)
+          // the icnt-th item of this CTA lives in accumulator icnt & (NACC - 1) (see the MMA issuers); this group
+          // drains the accumulators of its parity
           if ((int)(icnt & 1) != grp) continue;
+          const uint32_t acc = icnt & (NACC - 1u);
+          const uint32_t tacc = tacc0 + ACCW * acc;
+          const uint32_t bfull = bar(CT_FULL0 + (int)acc), drained = sBar + 8u * C_COUNT + 16u + 4u * acc;
           // everything that does not depend on the accumulator first: its latency hides behind the wait
           float c = ch;
           bool off = false;
@@ -1377,16 +1584,16 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
             off = actg[s] != nullptr && !__ldg(actg[s] + k);
           }
           const float e = fmaf(ek, xn[s], ea);
-          mbar_wait(bfull, (icnt >> 1) & 1, err);
+          mbar_wait(bfull, (icnt >> LGA) & 1, err);
           tc_fence_after();
-          uint32_t r[128];
+          uint32_t r[DIM];
           tmem_ld64(tacc, r);
-          tmem_ld64(tacc + 64u, r + 64);
+          if constexpr (DIM == 128) tmem_ld64(tacc + 64u, r + 64);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           tc_fence_before();
           __syncwarp();
           if (lane == 0) asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(drained) : "memory");
-          const float ss = sumsq128(r);
+          const float ss = sumsq_regs<DIM>(r);
           if (qrow[s] != nullptr) {
             float d;
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(d) : "f"(ss * cinv2));
@@ -1582,9 +1789,37 @@ build_items_kernel(const int32_t* __restrict__ itoff, const long long* __restric
 __global__ void __launch_bounds__(256)
 gather_list_q_kernel(const float* __restrict__ q, int64_t ldq, const int32_t* __restrict__ lrow,
                      const long long* __restrict__ koff, const long long* __restrict__ kcnt, float* __restrict__ lq,
-                     double* __restrict__ Nk) {
+                     double* __restrict__ Nk, const int32_t* __restrict__ gid, int K) {
   const int k = blockIdx.y;
   const long long cnt = kcnt[k], base = koff[k];
+  if (gid != nullptr) {
+    // grouped model: Nk is [J][K].  The lists are in row order and rows are grouped, so a warp nearly always sees
+    // one group: one warp reduction and one atomic per 32 entries; a warp that straddles a group boundary adds
+    // entry by entry.
+    const int lane = threadIdx.x & 31;
+    for (long long e0 = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); e0 < cnt;
+         e0 += (long long)gridDim.x * blockDim.x) {
+      const long long e = e0 + lane;
+      const bool valid = e < cnt;
+      float v = 0.f;
+      int g = -1;
+      if (valid) {
+        const int32_t row = lrow[base + e];
+        v = q[(int64_t)row * ldq + k];
+        lq[base + e] = v;
+        g = gid[row];
+      }
+      const int g0 = __shfl_sync(0xffffffffu, g, 0);
+      if (__all_sync(0xffffffffu, !valid || g == g0)) {
+        double a = (double)v;
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0 && a != 0.0) atomicAdd(&Nk[(size_t)g0 * K + k], a);
+      } else if (valid && v != 0.f) {
+        atomicAdd(&Nk[(size_t)g * K + k], (double)v);
+      }
+    }
+    return;
+  }
   double acc = 0;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < cnt; e += (long long)gridDim.x * blockDim.x) {
     const float v = q[(int64_t)lrow[base + e] * ldq + k];
@@ -1602,14 +1837,20 @@ gather_list_q_kernel(const float* __restrict__ q, int64_t ldq, const int32_t* __
   }
 }
 
-// Euclidean norm of every (centred) row, D == 128: one warp per row, float4 per lane
+// Euclidean norm of every (centred) row, D == 128 or 64: one warp per row, float4 (float2) per lane
 __global__ void __launch_bounds__(256)
-row_norm128_kernel(const float* __restrict__ X, int64_t N, float* __restrict__ out) {
+row_norm128_kernel(const float* __restrict__ X, int64_t N, float* __restrict__ out, int dim) {
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   for (int64_t n = warp0; n < N; n += nwarps) {
-    const float4 v = __ldg(reinterpret_cast<const float4*>(X + n * kD) + lane);
+    float4 v;
+    if (dim == 128) {
+      v = __ldg(reinterpret_cast<const float4*>(X + n * 128) + lane);
+    } else {
+      const float2 h = __ldg(reinterpret_cast<const float2*>(X + n * 64) + lane);
+      v = make_float4(h.x, h.y, 0.f, 0.f);
+    }
     float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) out[n] = sqrtf(s);
@@ -1619,18 +1860,21 @@ row_norm128_kernel(const float* __restrict__ X, int64_t N, float* __restrict__ o
 }  // namespace
 
 bool tc_supported(int D, int64_t ldx) { return D == 128 && ldx == 128; }
+int tc_dim(int D, int64_t ldx) { return (D == 128 && ldx == 128) ? 128 : (D == 64 && ldx == 64) ? 64 : 0; }
 
 cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err,
-                        const unsigned* skip) {
+                        const unsigned* skip, int dim) {
   if (N <= 0) return cudaSuccess;
-  cudaError_t e = cudaFuncSetAttribute(estep_tc128_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  if (dim != 128 && dim != 64) return cudaErrorInvalidValue;
+  auto kern = dim == 128 ? estep_tc128_kernel<false, 128> : estep_tc128_kernel<false, 64>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ntiles = (N + kTM - 1) / kTM;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  estep_tc128_kernel<false><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q,
-                                                                  ldq, Fz, err, nullptr, nullptr, 0, nullptr, skip);
+  kern<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, act, q, ldq, Fz, err, nullptr,
+                                             nullptr, 0, nullptr, skip);
   return cudaGetLastError();
 }
 
@@ -1638,19 +1882,20 @@ cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N
                              const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                              const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
                              const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err,
-                             const long long* nitems_dev, const unsigned* skip) {
+                             const long long* nitems_dev, const unsigned* skip, int dim) {
   if (N <= 0 || (nitems <= 0 && nitems_dev == nullptr)) return cudaSuccess;
+  if (dim != 128 && dim != 64) return cudaErrorInvalidValue;
   // nitems_dev != NULL: the item count lives on the device; `nitems` is then the capacity of `items`
   const int64_t bgrid = nitems_dev ? (int64_t)sms * 8 : (nitems + 255) / 256;
   build_items_kernel<<<(unsigned)bgrid, 256, 0, st>>>(itoff, koff, kcnt, K, nitems, (int4*)items, nitems_dev, skip);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(estep_tc128_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  auto kern = dim == 128 ? estep_tc128_kernel<true, 128> : estep_tc128_kernel<true, 64>;
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;
   const int grid = (int)(nitems < sms && nitems_dev == nullptr ? nitems : sms);
-  estep_tc128_kernel<true><<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, nullptr, q,
-                                                                 ldq, nullptr, err, lrow, (const int4*)items, nitems,
-                                                                 nitems_dev, skip);
+  kern<<<grid, kThreadsTc, kSmemBytes, st>>>(X, N, gid, K, blob, ascale, inv_t2, chat, lw, nullptr, q, ldq, nullptr, err,
+                                             lrow, (const int4*)items, nitems, nitems_dev, skip);
   return cudaGetLastError();
 }
 
@@ -1658,17 +1903,17 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
                                float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
-                               unsigned* err, const unsigned* augh_dev, const unsigned* skip) {
+                               unsigned* err, const unsigned* augh_dev, const unsigned* skip, int dim) {
   if (N <= 0) return cudaSuccess;
-  if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(estep_coarse_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
+  if (K < 1 || K > kTcCoarseMaxK || aug_exp < 0 || aug_exp > 15 || (dim != 128 && dim != 64)) return cudaErrorInvalidValue;
+  auto kern = dim == 128 ? estep_coarse_tc128_kernel<128> : estep_coarse_tc128_kernel<64>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCSmemBytes);
   if (e != cudaSuccess) return e;
   const int64_t ngroups = (N + kCRows - 1) / kCRows;
   const int grid = (int)(ngroups < sms ? ngroups : sms);
   const uint32_t h = (uint32_t)__half_as_ushort(__float2half_rn(ldexpf(1.f, aug_exp)));
-  estep_coarse_tc128_kernel<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg,
-                                                                   h | (h << 16), h, margin, q, ldq, cmask, sbase_hint, err,
-                                                                   augh_dev, skip);
+  kern<<<grid, kThreadsTc, kCSmemBytes, st>>>(X, xnorm, N, gid, K, blob, augblob, cpar, lw, act, sg, h | (h << 16), h,
+                                              margin, q, ldq, cmask, sbase_hint, err, augh_dev, skip);
   return cudaGetLastError();
 }
 
@@ -1708,20 +1953,22 @@ cudaError_t mask_fill(cudaStream_t st, const uint32_t* cmask, int64_t N, int K, 
 }
 
 cudaError_t gather_list_q(cudaStream_t st, int sms, const float* q, int64_t ldq, const int32_t* lrow,
-                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk) {
+                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk,
+                          const int32_t* gid) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
   long long bx = (maxcnt + 255) / 256;
   const long long cap = std::max<long long>(1, (long long)sms * 8 / K);
   if (bx > cap) bx = cap;
-  gather_list_q_kernel<<<dim3((unsigned)bx, (unsigned)K), 256, 0, st>>>(q, ldq, lrow, koff, kcnt, lq, Nk);
+  gather_list_q_kernel<<<dim3((unsigned)bx, (unsigned)K), 256, 0, st>>>(q, ldq, lrow, koff, kcnt, lq, Nk, gid, K);
   return cudaGetLastError();
 }
 
-cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out) {
+cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out, int dim) {
   if (N <= 0) return cudaSuccess;
+  if (dim != 128 && dim != 64) return cudaErrorInvalidValue;
   const int64_t want = (N + 7) / 8;
   const int grid = (int)(want < (int64_t)sms * 16 ? want : (int64_t)sms * 16);
-  row_norm128_kernel<<<grid, 256, 0, st>>>(X, N, out);
+  row_norm128_kernel<<<grid, 256, 0, st>>>(X, N, out, dim);
   return cudaGetLastError();
 }
 
@@ -1752,19 +1999,25 @@ double tc_pack_aug(const double* w /* [128] */, int k, uint8_t* augblob) {
 cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t* lrow, const float* lq,
                         const long long* koff, const long long* kcnt, long long maxcnt, long long nnz, int K,
                         const float* cen, float scale, double* xs, double* S, unsigned* err, const float* scale_dev,
-                        const unsigned* skip) {
+                        const unsigned* skip, int dim) {
   if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  static const int pf = [] {
+    const char* e = std::getenv("LCB_SSTAT_PREFETCH");  // 0 none, 1 prefetch.global.L2 by an idle warp, 2 bulk prefetch
+    return e ? std::atoi(e) : 0;
+  }();
+  if (dim != 128 && dim != 64) return cudaErrorInvalidValue;
   // rows folded into one fp32 TMEM accumulator before the fp64 add: fewer for small problems (more accurate, and the
   // extra atomics are free there), kTcScatterChunk for large ones
   const int chunk_rows = nnz <= (1LL << 20) ? 128 : kTcScatterChunk;
-  cudaError_t e = cudaFuncSetAttribute(sstat_tc128_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes);
+  auto kern = dim == 128 ? sstat_tc128_kernel<128> : sstat_tc128_kernel<64>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSSmemBytes);
   if (e != cudaSuccess) return e;
   // persistent CTAs walk the (cluster, chunk) items; no more CTAs than items
   const long long items_max = (nnz + chunk_rows - 1) / chunk_rows + K;
   if (K > kTcCoarseMaxK || items_max > 2000000000LL) return cudaErrorInvalidValue;
   const int grid = (int)(items_max < sms ? items_max : sms);
-  sstat_tc128_kernel<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, K, cen, scale, chunk_rows, xs,
-                                                                 S, err, scale_dev, skip);
+  kern<<<grid, kScatterThreads, kSSmemBytes, st>>>(X, lrow, lq, koff, kcnt, K, cen, scale, chunk_rows, xs, S, err, scale_dev,
+                                                   skip, pf);
   return cudaGetLastError();
 }
 

@@ -11,11 +11,15 @@ constexpr uint32_t kTcBlobBytes = 50176;  // pre-swizzled fp16 hi/lo operand of 
 
 // true when the fp32 engine can run the full-covariance E step on the tensor cores
 bool tc_supported(int D, int64_t ldx);
+// 128 or 64 when the device-resident iteration (engine_dev.cu) can run the tcgen05 kernels on rows of that width,
+// else 0.  Every tensor-core launcher below takes that width as its last argument (`dim`, default 128); 64-wide rows
+// use the same operand blobs with R_k in the upper-left 64 x 64 corner (mstep.cu) and skip everything above it.
+int tc_dim(int D, int64_t ldx);
 
 cudaError_t estep_tc128(cudaStream_t st, int sms, const float* X, int64_t N, const int32_t* gid, int K,
                         const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                         const float* lw, const uint8_t* act, float* q, int64_t ldq, double* Fz, unsigned* err,
-                        const unsigned* skip = nullptr);
+                        const unsigned* skip = nullptr, int dim = 128);
 // Device-driven variants (mstep.cuh): `skip` points at a control word; the kernel returns at once when it is set
 // (the two-level kernels look at skip[0] | skip[1]: aborted iteration, or the dense kernel takes over).
 
@@ -30,7 +34,8 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
                                const int32_t* gid, int K, const uint8_t* blob, const uint8_t* augblob,
                                const float* cpar, const float* lw, const uint8_t* act, float sg, int aug_exp,
                                float margin, float* q, int64_t ldq, uint32_t* cmask, uint32_t sbase_hint,
-                               unsigned* err, const unsigned* augh_dev = nullptr, const unsigned* skip = nullptr);
+                               unsigned* err, const unsigned* augh_dev = nullptr, const unsigned* skip = nullptr,
+                               int dim = 128);
 // err[1] of a launch whose sbase_hint did not match: 0x80000000 | the 1024-aligned shared-memory base to pass instead
 constexpr uint32_t kTcSbaseDefault = 1024;
 // candidate masks -> per-cluster row lists: mask_count, nz_scan (kernels.cuh), mask_fill
@@ -44,16 +49,18 @@ cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N
                              const uint8_t* blob, const float* ascale, const float* inv_t2, const float* chat,
                              const float* lw, const int32_t* lrow, const long long* koff, const long long* kcnt,
                              const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err,
-                             const long long* nitems_dev = nullptr, const unsigned* skip = nullptr);
+                             const long long* nitems_dev = nullptr, const unsigned* skip = nullptr, int dim = 128);
 // level 3: q = softmax over the candidate logits (0 elsewhere), Fz += sum log Z
 cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
                            double* Fz, const unsigned* skip = nullptr);
 // q = -inf outside the candidate mask (test modes only)
 cudaError_t apply_candidate_mask(cudaStream_t st, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask);
-// lq[e] = q[lrow[e]][k] over the lists, Nk[k] += sum: lets the statistics pass reuse the candidate lists
+// lq[e] = q[lrow[e]][k] over the lists, Nk[k] += sum (grouped models, gid != NULL: Nk[gid[row]][k]): lets the
+// statistics pass reuse the candidate lists
 cudaError_t gather_list_q(cudaStream_t st, int sms, const float* q, int64_t ldq, const int32_t* lrow,
-                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk);
-cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out);
+                          const long long* koff, const long long* kcnt, long long maxcnt, int K, float* lq, double* Nk,
+                          const int32_t* gid = nullptr);
+cudaError_t row_norm128(cudaStream_t st, int sms, const float* X, int64_t N, float* out, int dim = 128);
 double tc_pack_aug(const double* w, int k, uint8_t* augblob);
 
 // Centred scatter over the per-cluster non-zero lists (see tc_kernels.cu); cen [K][128] is relative to the data
@@ -62,7 +69,7 @@ constexpr int kTcScatterChunk = 512;  // list rows folded into the fp32 accumula
 cudaError_t sstat_tc128(cudaStream_t st, int sms, const float* X, const int32_t* lrow, const float* lq,
                         const long long* koff, const long long* kcnt, long long maxcnt, long long nnz, int K,
                         const float* cen, float scale, double* xs, double* S, unsigned* err,
-                        const float* scale_dev = nullptr, const unsigned* skip = nullptr);
+                        const float* scale_dev = nullptr, const unsigned* skip = nullptr, int dim = 128);
 
 void tc_pack_cluster(const double* R, double bscale, const double* mean_rel, double ascale, uint8_t* out);
 int tc_pack_selftest();  // bytes differing between the F16C and the portable packing of one operand

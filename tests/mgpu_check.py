@@ -1,5 +1,8 @@
-"""Run under torchrun on >= 2 GPUs (not collected by pytest): row-sharded VB iterations with the
-NCCL all-reduce must reproduce the single-GPU F trace and statistics."""
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_multirank.py launches it when the box has them): row-sharded VB
+iterations with the NCCL all-reduce must reproduce the single-GPU F trace, posteriors and qZ -- flat models, a
+grouped model with whole groups per rank (SURVEY.md 8e, config 4's partitioning) and a full learn() with splits.
+LCB_HOST_MSTEP=1 LCB_DIST_MSTEP=1 in the environment runs the same checks through the host M step with the
+factorisations split over the ranks."""
 import os
 import sys
 
@@ -44,6 +47,40 @@ def main():
             print("model", model, "D", D, "F", F[-1], "ref", ref[0][-1], "OK" if good else "MISMATCH", flush=True)
             ok = ok and good
         eng.close()
+    # grouped model (learnGMC: GDirichlet weights per group, shared GaussWish clusters), whole groups per rank:
+    # every rank passes all J groups, the ones it does not own with zero rows
+    for (D, K, J, N) in [(128, 9, 6, 24000), (5, 4, 7, 7000)]:
+        X, z = make_blobs(N, D, K, seed=J, spread=4.0)
+        cuts = np.linspace(0, N, J + 1).astype(int)
+        groups = [X[cuts[j]:cuts[j + 1]] for j in range(J)]
+        q0 = soft_labels(z, K, seed=4)
+        ref = None
+        if rank == 0:
+            e1 = lc.Engine(local, lc.F32)
+            e1.set_data(groups); e1.model_init(lc.GMC); e1.set_qz(q0); e1.vbem(maxit=3)
+            ref = (e1.trace()[0], [e1.group_weights(j)[1] for j in range(J)], e1.qZ())
+            e1.close()
+        eng = lc.Engine(local, lc.F32)
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(lc.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        eng.comm_init_nccl(bytes(idt.cpu().numpy().tobytes()), rank, world)
+        jb, je = lc.shard_rows(J, rank, world)
+        mine = [groups[j] if jb <= j < je else groups[j][:0] for j in range(J)]
+        q0m = np.concatenate([q0[cuts[j]:cuts[j + 1]] for j in range(jb, je)] + [q0[:0]], 0)
+        eng.set_data(mine); eng.model_init(lc.GMC); eng.set_qz(q0m); eng.vbem(maxit=3)
+        F = eng.trace()[0]
+        ew = [eng.group_weights(j)[1] for j in range(J)]
+        qs = eng.qZ()
+        good = len(F) == 4
+        if rank == 0:
+            good = (good and len(F) == len(ref[0]) and np.allclose(F, ref[0], rtol=1e-6)
+                    and all(np.allclose(a, b, atol=1e-5) for a, b in zip(ew, ref[1]))
+                    and all(np.abs(qs[j] - ref[2][j]).max() < 1e-5 for j in range(jb, je)))
+            print("GMC D", D, "K", K, "J", J, "F", F[-1], "ref", ref[0][-1], "OK" if good else "MISMATCH", flush=True)
+            ok = ok and good
+        eng.close()
     # full learn with splits, sharded
     X, _ = make_blobs(4000, 3, 4, seed=5, spread=8.0)
     eng = lc.Engine(local, lc.F32)
@@ -67,7 +104,8 @@ def main():
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:
-        print("MGPU_CHECK", "PASS" if ok else "FAIL", flush=True)
+        print("MGPU_CHECK", "PASS" if ok else "FAIL", "world", world, "host_mstep", os.environ.get("LCB_HOST_MSTEP", "0"),
+              "dist_mstep", os.environ.get("LCB_DIST_MSTEP", "auto"), flush=True)
 
 
 if __name__ == "__main__":

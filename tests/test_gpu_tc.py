@@ -51,31 +51,38 @@ def test_tc_estep_matches_oracle_and_simt(N, K, spread):
     assert np.abs(res[True][1] - res[False][1]).max() <= 5e-6
 
 
-def test_tc_overlapping_clusters_known_limit():
-    """Two heavily overlapping clusters in 128-D, far from the origin -- the hardest case for fp32: logit ~ -64
-    multiplies any relative error of the covariance estimate by 64.  Documented limit: the fp32
-    engine stays within 1e-4 on qZ and 1e-5 on F here (1e-5 on qZ everywhere else in this suite); the fp64 engine
-    reproduces the oracle to 1e-8."""
+def test_tc_overlapping_clusters():
+    """Two heavily overlapping clusters in 128-D, far from the origin -- the hardest case for fp32: logits of about -100
+    whose difference decides q, so q carries the fp32 resolution of the logits (ulp(100) = 7.6e-6).
+    * one VB iteration from the same responsibilities (the E step proper): the fp32 engine holds the stated 1e-5 on qZ
+      and 1e-5 on F;
+    * the map q -> q' of this ill-conditioned mixture is expansive: over four iterations the per-iteration error grows
+      to 2.5e-5 .. 5.3e-5 for EVERY fp32 arithmetic -- the tensor-core path, the SIMT statistics pass with the
+      tensor-core E pass, and the pure fp32 CUDA-core path alike (profiles/diag_overlap_r02.log, tools/diag_overlap.py),
+      i.e. it is a property of fp32, not of the fp16-split tensor-core scheme.  Bound held here: 1e-4 on qZ after four
+      iterations, 1e-5 on F;
+    * the fp64 engine reproduces the oracle to 1e-8 over the four iterations."""
     rng = np.random.default_rng(0)
     D, N = 128, 6000
     base = rng.uniform(-20, 20, size=D)
     X = np.concatenate([base + rng.normal(size=(N // 2, D)), base + 0.15 + 1.05 * rng.normal(size=(N // 2, D))])
     z = np.repeat([0, 1], N // 2)
     q0 = soft_labels(z, 2, seed=1, noise=0.6)
-    m = po.Model(po.VDP, [X])
-    m.vbem(q0, maxit=3)
-    qo = m.qZ()
-    assert ((qo > 0.05) & (qo < 0.95)).mean() > 0.1          # genuinely soft assignments
-    for prec, tol_q, tol_f in ((lc.F32, 1e-4, 1e-5), (lc.F64, 1e-8, 1e-9)):
-        eng = lc.Engine(0, prec)
-        eng.set_data(X)
-        eng.model_init(lc.VDP)
-        eng.set_qz(q0)
-        eng.vbem(maxit=3)
-        dq = np.abs(eng.qZ(0) - qo).max()
-        dF = np.abs(eng.trace()[0] / m.trace()[0] - 1).max()
-        assert dq <= tol_q and dF <= tol_f, (prec, dq, dF)
-        eng.close()
+    for maxit in (0, 3):
+        m = po.Model(po.VDP, [X])
+        m.vbem(q0, maxit=maxit)
+        qo = m.qZ()
+        assert ((qo > 0.05) & (qo < 0.95)).mean() > 0.1          # genuinely soft assignments
+        for prec, tol_q, tol_f in ((lc.F32, 1e-5 if maxit == 0 else 1e-4, 1e-5), (lc.F64, 1e-8, 1e-9)):
+            eng = lc.Engine(0, prec)
+            eng.set_data(X)
+            eng.model_init(lc.VDP)
+            eng.set_qz(q0)
+            eng.vbem(maxit=maxit)
+            dq = np.abs(eng.qZ(0) - qo).max()
+            dF = np.abs(eng.trace()[0] / m.trace()[0] - 1).max()
+            assert dq <= tol_q and dF <= tol_f, (maxit, prec, dq, dF)
+            eng.close()
 
 
 def test_tc_grouped_sparse_and_full_learn():
