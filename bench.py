@@ -406,7 +406,10 @@ def main():
         kname, kms = "estep_coarse_tc128_kernel", coarse_ms / a.steps
         # ncu --set full at N=4M (profiles/ncu_r01_coarse_v4_raw.csv): dram read 2.12 GB + write 1.07 GB per launch
         # = 799 B / point (algorithmic: 512 B of X, 256 B of level-1 bounds, 8 B of candidate mask)
-        traffic = 799.0 * nloc if D == 128 else None
+        # dram__bytes_read + dram__bytes_write of one ncu --set full capture of this kernel at N = 4 M
+        # (profiles/ncu_r02_coarse128_summary.txt: 2.1165 GB + 1.0651 GB = 795 B / point; algorithmic: 512 B of X,
+        # 256 B of level-1 bounds parked in q, 8 B of candidate mask), scaled to this run's rows
+        traffic = (2.116509e9 + 1.065072e9) / 4.0e6 * nloc if D == 128 else None
         levels = {k_: (lv[k_] / a.steps) for k_ in ("coarse_ms", "lists_ms", "refine_ms", "finalize_ms")}
         levels["candidate_pairs_per_row"] = lv["pairs"] / a.steps / max(nloc, 1)
     elif e_ms >= s_ms:
@@ -418,14 +421,23 @@ def main():
         traffic = None
     peak_tf = pk.get("bf16_tflops_sustained", pk.get("bf16_tflops"))
     ach_tf = flops_half / (kms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": ach_tf / peak_tf, "traffic": traffic, "peak_source": pk["_source"] + " bf16_tflops_sustained",
+    if diag:
+        # diagonal models are bound by the read of X (4 D bytes per point and pass); the dominant kernel is
+        # the SIMT E pass (DESIGN.md section 5, config 5 analysis)
+        kname, kms = ("estep_diag_kernel", e_ms / a.steps) if e_ms >= s_ms else ("nz lists + sstat_gather_diag_kernel", s_ms / a.steps)
+        ach_gbs = 4.0 * D * nloc / (kms * 1e-3) / 1e9
+    roofline = {"bound": "hbm" if diag else "tensor", "kernel": kname, "achieved": ach_gbs if diag else ach_tf,
+                "peak": pk["hbm_gbs"] if diag else peak_tf, "unit": "GB/s" if diag else "TFLOP/s",
+                "frac": (ach_gbs / pk["hbm_gbs"]) if diag else ach_tf / peak_tf, "traffic": traffic,
+                "peak_source": pk["_source"] + (" hbm_gbs" if diag else " bf16_tflops_sustained"),
                 "kernel_ms": kms, "hbm_frac": (4.0 * (D + K) * nloc / (kms * 1e-3) / 1e9) / pk["hbm_gbs"],
                 "sstat_ms": s_ms / a.steps, "estep_ms": e_ms / a.steps, "estep_levels": levels,
                 "note": ("achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
                          "level-1 kernel of the two-level E pass (one fp16 product per pair, 0.69 x 2 executed tensor "
                          "flop per algorithmic flop incl. the centring chunk); exact logits are recomputed only for "
                          "the candidate pairs (estep_levels)" if levels else
+                         ("achieved = algorithmic 4*D bytes/point x points / event time of the dominant pass (diagonal "
+                          "model: HBM-bound in principle, SIMT E pass in practice, DESIGN.md section 5)") if diag else
                          "achieved = algorithmic K*D^2 flop/point (triangular whitening) x points / event time of the "
                          "E-pass kernel; the fp16 hi/lo scheme executes 3 x 0.56 x 2 = 3.4 tensor flop per algorithmic "
                          "flop, so tensor-pipe utilisation is higher than frac (ncu: profiles/)")}

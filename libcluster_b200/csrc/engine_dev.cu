@@ -184,7 +184,9 @@ void Engine::dev_sphase(View& v) {
   const bool tc_s = full && prec_ == kF32 && use_tc_ && use_tc_sstat_ && tdim != 0 && K <= dev::kTcCoarseMaxK;
   const bool reuse = list_valid_ && list_q_ == v.q && list_K_ == K && list_N_ == v.N && tc_s && !sparse_;
   list_valid_ = false;
-  const bool fuse_counts = full && !sparse_ && v.N > 0;  // nz_count / gather_list_q produce Njk in the same sweep
+  // diagonal models take the list route too (the statistics of the listed pairs only) up to 1024 dimensions
+  const bool lists = full || D <= 1024;
+  const bool fuse_counts = lists && !sparse_ && v.N > 0;  // nz_count / gather_list_q produce Njk in the same sweep
   if (!fuse_counts) {
     if (prec_ == kF32) check(dev::colsum<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
     else check(dev::colsum<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_njk), "colsum");
@@ -203,7 +205,7 @@ void Engine::dev_sphase(View& v) {
     act_.clear();
   }
   cudaError_t ke = cudaSuccess;
-  if (full && v.N > 0) {
+  if (lists && v.N > 0) {
     long long* d_tot = (long long*)d_nzoff_.p;
     if (reuse) {
       // the candidate lists of the last E pass cover every non-zero of q
@@ -245,7 +247,10 @@ void Engine::dev_sphase(View& v) {
       if (prec_ == kF32) {
         check(dev::nz_fill<float>(stream_, (const float*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (float*)lq,
                                   dev::kNzNonZero, skipS), "nz_fill");
-        if (tc_s)
+        if (!full)
+          ke = dev::sstat_gather_diag<float>(stream_, (const float*)v.X, D, v.ldx, lrow, (const float*)lq, d_koff, d_tot,
+                                             (long long)v.N, K, (const float*)d_cen_.p, d_xs, d_S, skipS);
+        else if (tc_s)
           ke = dev::sstat_tc128(stream_, sms_, (const float*)v.X, lrow, (const float*)lq, d_koff, d_tot, (long long)v.N,
                                 nnz_hint, K, (const float*)d_cen_.p, 0.f, d_xs, d_S, (unsigned*)d_err_.p, d_sscale, skipS,
                                 tdim);
@@ -255,12 +260,16 @@ void Engine::dev_sphase(View& v) {
       } else {
         check(dev::nz_fill<double>(stream_, (const double*)v.q, v.ldq, v.N, K, v.gid, d_act, d_cnt, d_koff, lrow, (double*)lq,
                                    dev::kNzNonZero, skipS), "nz_fill");
-        ke = dev::sstat_gather_full<double>(stream_, (const double*)v.X, D, v.ldx, lrow, (const double*)lq, d_koff, d_tot,
-                                            (long long)v.N, K, (const double*)d_cen_.p, d_xs, d_S, skipS);
+        if (!full)
+          ke = dev::sstat_gather_diag<double>(stream_, (const double*)v.X, D, v.ldx, lrow, (const double*)lq, d_koff, d_tot,
+                                              (long long)v.N, K, (const double*)d_cen_.p, d_xs, d_S, skipS);
+        else
+          ke = dev::sstat_gather_full<double>(stream_, (const double*)v.X, D, v.ldx, lrow, (const double*)lq, d_koff, d_tot,
+                                              (long long)v.N, K, (const double*)d_cen_.p, d_xs, d_S, skipS);
       }
       launches_ += 2;
     }
-  } else if (!full) {
+  } else if (!full && v.N > 0) {
     if (prec_ == kF32)
       ke = dev::sstat_diag<float>(stream_, (const float*)v.X, v.N, D, v.ldx, v.gid, (const float*)v.q, v.ldq, K,
                                   (const float*)d_cen_.p, d_act, d_xs, d_S);

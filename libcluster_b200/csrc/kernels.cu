@@ -13,6 +13,7 @@
 // fp64 exact path.  The tcgen05 tier for D in {64,128} lives in tc_kernels.cu.
 #include "kernels.cuh"
 
+#include <algorithm>
 #include <cfloat>
 #include <cmath>
 
@@ -279,6 +280,43 @@ estep_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
           Ml[dd * KS + kk] = l;
         }
         __syncthreads();
+        if constexpr (sizeof(T) == 4) {
+          // fp32: packed f32x2 instructions, two clusters per lane-operation (the loop is bound by the issue rate of
+          // its four floating-point instructions per (point, cluster, dimension); the same IEEE operations as below)
+#pragma unroll 4
+          for (int dd = 0; dd < DC; ++dd) {
+            const float4 xv = *reinterpret_cast<const float4*>(Xch + dd * XS + ty * 4);
+            const float4 av = *reinterpret_cast<const float4*>(Ach + dd * KS + tx * 4);
+            const float4 hv = *reinterpret_cast<const float4*>(Mh + dd * KS + tx * 4);
+            const float4 lv = *reinterpret_cast<const float4*>(Ml + dd * KS + tx * 4);
+            const float xs4[4] = {xv.x, xv.y, xv.z, xv.w};
+            unsigned long long a2[2], h2[2], l2[2];
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a2[0]) : "f"(av.x), "f"(av.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(a2[1]) : "f"(av.z), "f"(av.w));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(h2[0]) : "f"(hv.x), "f"(hv.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(h2[1]) : "f"(hv.z), "f"(hv.w));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(l2[0]) : "f"(lv.x), "f"(lv.y));
+            asm("mov.b64 %0, {%1, %2};" : "=l"(l2[1]) : "f"(lv.z), "f"(lv.w));
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+              unsigned long long x2;
+              asm("mov.b64 %0, {%1, %1};" : "=l"(x2) : "f"(xs4[p]));
+#pragma unroll
+              for (int cp = 0; cp < 2; ++cp) {
+                unsigned long long t2, u2, acc2;
+                asm("mov.b64 %0, {%1, %2};" : "=l"(acc2) : "f"((float)acc[p][2 * cp]), "f"((float)acc[p][2 * cp + 1]));
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(x2), "l"(h2[cp]));
+                asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t2) : "l"(t2), "l"(l2[cp]));
+                asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(u2) : "l"(a2[cp]), "l"(t2));
+                asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2) : "l"(u2), "l"(t2));
+                float r0, r1;
+                asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(acc2));
+                acc[p][2 * cp] = (T)r0;
+                acc[p][2 * cp + 1] = (T)r1;
+              }
+            }
+          }
+        } else {
 #pragma unroll 4
         for (int dd = 0; dd < DC; ++dd) {
           T x[4], a[4], h[4], l[4];
@@ -297,6 +335,7 @@ estep_diag_kernel(const T* __restrict__ X, int64_t N, int D, int64_t ldx, const 
               const T t = (x[p] - h[c]) - l[c];
               acc[p][c] = fma(a[c] * t, t, acc[p][c]);
             }
+        }
         }
       }
 #pragma unroll
@@ -638,6 +677,99 @@ sstat_gather_full_kernel(const T* __restrict__ X, int D, int64_t ldx, const int3
     if (v != 0.0) atomicAdd(&xs[(size_t)k * D + i0 + tid], v);
   }
   __syncthreads();
+  }
+}
+
+// Sufficient statistics, diagonal, over the per-cluster lists of non-zero responsibilities (the lists of the
+// full-covariance pass: nz_count / nz_scan / nz_fill):  xs_k += sum_e q_e (x_e - c_k),  S_k += sum_e q_e (x_e - c_k)^2.
+// q is numerically sparse, so the pass costs one gathered read of every listed row (2 D flop per pair) instead of
+// the K * D products per row of the dense kernel below -- at one pair per row it is bound by the read of X.
+// A CTA takes chunks of one cluster's list; thread t owns dimensions t, t + kThreads, ... (D <= 4 * kThreads); fp32
+// sums over 64 entries are folded into fp64 registers, one fp64 atomic per (cluster, dimension, CTA) at the end.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+sstat_gather_diag_kernel(const T* __restrict__ X, int D, int64_t ldx, const int32_t* __restrict__ lrow,
+                         const T* __restrict__ lq, const long long* __restrict__ koff,
+                         const long long* __restrict__ kcnt, const T* __restrict__ cen, double* __restrict__ xs,
+                         double* __restrict__ S, const unsigned* __restrict__ skip) {
+  if (skip != nullptr && *skip != 0u) return;
+  constexpr int kChunk = 1024, kFold = 64, kDims = 4;
+  const int k = blockIdx.y, tid = threadIdx.x;
+  const long long cnt = kcnt[k], base = koff[k];
+  T c[kDims];
+  double A1[kDims], A2[kDims];
+#pragma unroll
+  for (int j = 0; j < kDims; ++j) {
+    const int d = tid + j * kThreads;
+    c[j] = d < D ? cen[(size_t)k * D + d] : (T)0;
+    A1[j] = 0;
+    A2[j] = 0;
+  }
+  bool any = false;
+  for (long long l0 = (long long)blockIdx.x * kChunk; l0 < cnt; l0 += (long long)gridDim.x * kChunk) {
+    const long long l1 = l0 + kChunk < cnt ? l0 + kChunk : cnt;
+    any = true;
+    for (long long f0 = l0; f0 < l1; f0 += kFold) {
+      const int nf = (int)(f0 + kFold < l1 ? kFold : l1 - f0);
+      T s1[kDims], s2[kDims];
+#pragma unroll
+      for (int j = 0; j < kDims; ++j) {
+        s1[j] = 0;
+        s2[j] = 0;
+      }
+      int e = 0;
+      for (; e + 4 <= nf; e += 4) {  // four rows in flight per thread and dimension
+        int32_t r[4];
+        T w[4], xv[4][kDims];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          r[u] = __ldg(lrow + base + f0 + e + u);
+          w[u] = __ldg(lq + base + f0 + e + u);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < kDims; ++j) {
+            const int d = tid + j * kThreads;
+            xv[u][j] = d < D ? __ldg(X + (size_t)r[u] * ldx + d) : (T)0;
+          }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < kDims; ++j) {
+            const T xc = xv[u][j] - c[j];
+            const T t = w[u] * xc;
+            s1[j] += t;
+            s2[j] = fma(t, xc, s2[j]);
+          }
+      }
+      for (; e < nf; ++e) {
+        const int32_t r = __ldg(lrow + base + f0 + e);
+        const T w = __ldg(lq + base + f0 + e);
+#pragma unroll
+        for (int j = 0; j < kDims; ++j) {
+          const int d = tid + j * kThreads;
+          const T xc = (d < D ? __ldg(X + (size_t)r * ldx + d) : (T)0) - c[j];
+          const T t = w * xc;
+          s1[j] += t;
+          s2[j] = fma(t, xc, s2[j]);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kDims; ++j) {
+        A1[j] += (double)s1[j];
+        A2[j] += (double)s2[j];
+      }
+    }
+  }
+  if (!any) return;
+#pragma unroll
+  for (int j = 0; j < kDims; ++j) {
+    const int d = tid + j * kThreads;
+    if (d < D) {
+      if (A1[j] != 0.0) atomicAdd(&xs[(size_t)k * D + d], A1[j]);
+      if (A2[j] != 0.0) atomicAdd(&S[(size_t)k * D + d], A2[j]);
+    }
   }
 }
 
@@ -1183,6 +1315,20 @@ cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, c
 }
 
 template <typename T>
+cudaError_t sstat_gather_diag(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
+                              const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
+                              double* xs, double* S, const unsigned* skip) {
+  if (K <= 0 || maxcnt <= 0) return cudaSuccess;
+  if (D > 4 * kThreads || K > 65535) return cudaErrorInvalidValue;
+  long long chunks = (maxcnt + 1023) / 1024;
+  const long long cap = std::max<long long>(1, 4096 / K);  // ~4096 CTAs in all; longer lists are strided over
+  if (chunks > cap) chunks = cap;
+  sstat_gather_diag_kernel<T><<<dim3((unsigned)chunks, (unsigned)K), kThreads, 0, st>>>(X, D, ldx, lrow, lq, koff, kcnt, cen,
+                                                                                       xs, S, skip);
+  return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t sstat_diag(cudaStream_t st, const T* X, int64_t N, int D, int64_t ldx, const int32_t* gid, const T* q,
                        int64_t ldq, int K, const T* cen, const uint8_t* act, double* xs, double* S) {
   if (N <= 0 || K <= 0) return cudaSuccess;
@@ -1324,6 +1470,9 @@ cudaError_t prune_columns(cudaStream_t st, T* q, int64_t ldq, int64_t N, const i
                                    int32_t*, double*, int);                                                           \
   template cudaError_t nz_fill<T>(cudaStream_t, const T*, int64_t, int64_t, int, const int32_t*, const uint8_t*,      \
                                   const int32_t*, const long long*, int32_t*, T*, int, const unsigned*);              \
+  template cudaError_t sstat_gather_diag<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \
+                                            const long long*, const long long*, long long, int, const T*, double*,   \
+                                            double*, const unsigned*);                                                \
   template cudaError_t sstat_gather_full<T>(cudaStream_t, const T*, int, int64_t, const int32_t*, const T*,           \
                                             const long long*, const long long*, long long, int, const T*, double*,   \
                                             double*, const unsigned*);                                                \

@@ -73,6 +73,12 @@ cudaError_t sstat_gather_full(cudaStream_t st, const T* X, int D, int64_t ldx, c
                               const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
                               double* xs, double* S, const unsigned* skip = nullptr);
 
+// the same for diagonal models: xs_k += sum q (x - c_k), S_k += sum q (x - c_k)^2 over the lists (D <= 1024)
+template <typename T>
+cudaError_t sstat_gather_diag(cudaStream_t st, const T* X, int D, int64_t ldx, const int32_t* lrow, const T* lq,
+                              const long long* koff, const long long* kcnt, long long maxcnt, int K, const T* cen,
+                              double* xs, double* S, const unsigned* skip = nullptr);
+
 // ---- data movement / labels / split bookkeeping ---------------------------
 // dst[n][d] = T(src[n][d] - mean[d]) from a staged block of doubles in either order
 template <typename T>
