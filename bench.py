@@ -545,13 +545,14 @@ def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
     torch.cuda.synchronize()
     Xn, qn = Xh.numpy(), qh.numpy()
     zd = torch.empty(nloc, dtype=torch.int32, device=dev)
-    times, times_it = [], []
+    times, times_it, times_up = [], [], []
     for i in range(1 + a.e2e_steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         eng.set_data(Xn)
+        tu = time.perf_counter()
         eng.model_init(lc.DGMM if a.model == "dgmm" else lc.BGMM)
         zd.copy_(zh, non_blocking=True)
         torch.cuda.synchronize()
@@ -563,6 +564,7 @@ def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
         if i > 0:
             times.append(t2 - t0)
             times_it.append(t1 - t0)
+            times_up.append(tu - t0)
     rowsum_err = float(np.abs(qn[: 1 << 16].sum(1) - 1.0).max())
     t = torch.tensor([float(np.mean(times)), float(np.mean(times_it))], dtype=torch.float64, device=dev)
     if world > 1:
@@ -571,6 +573,7 @@ def run_e2e(torch, dist, lc, eng, X, z, N, nloc, D, K, world, dev, a):
     return {"value": N / sec, "unit": "points/s", "h2d_bytes_per_step": int(need + nloc * 4),
             "d2h_bytes_per_step": int(need_q + 8), "ms_per_step": sec * 1e3, "steps": a.e2e_steps,
             "iteration_only_value": N / sec_it, "iteration_only_ms": sec_it * 1e3, "iteration_only_d2h_bytes": 8,
+            "upload_ms": float(np.mean(times_up)) * 1e3, "qz_emit_ms": (sec - sec_it) * 1e3,
             "qz_rowsum_max_err": rowsum_err,
             "path": "Engine.set_data(host fp64) + set_labels + lcb_vbem_step + lcb_get_qz (fp64, row-major, "
                     "page-locked destination) through the C ABI", "F": F}
