@@ -220,6 +220,26 @@ def cpu_iteration_rate(D, K, budget_s, reps=1, want="auto"):
     return rows, times, kind, (threads if kind == "reference" else 1)
 
 
+def blas_estimate(D, K, rows=8192):
+    """What the stand-in costs: the two O(N K D^2) halves of one iteration (src/distributions.cpp:301-313 addobs GEMM,
+    src/probutils.cpp:113-138 mahaldist solve) for `rows` rows with numpy's BLAS/LAPACK on all host threads -- the speed
+    a build of the reference against real Eigen (+ a threaded BLAS) could approach.  Context for cpu_baseline only."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(0)
+    X = rng.normal(size=(rows, D))
+    q = rng.uniform(size=(rows, K))
+    A = rng.normal(size=(D, D))
+    Lc = np.linalg.cholesky(A @ A.T / D + np.eye(D))
+    t0 = time.perf_counter()
+    for k in range(K):
+        (X * q[:, k:k + 1]).T @ X                                  # xx_s += qZkX^T X
+        y = sla.solve_triangular(Lc, (X - 0.1).T, lower=True)      # LDLT solve of mahaldist
+        (y * y).sum(0)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": "points/s", "rows": rows,
+            "what": "numpy/scipy BLAS timing of the GEMM and triangular-solve halves of one iteration (not the reference)"}
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -471,6 +491,10 @@ def main():
         if kind == "reference":
             r2, t2, _, _ = cpu_iteration_rate(D, K, budget_s=10.0, reps=1, want="port")
             cpu["port_value"] = r2 / t2[0]
+        try:
+            cpu["blas_estimate"] = blas_estimate(D, K)
+        except Exception as ex:  # noqa: BLE001
+            cpu["blas_estimate"] = {"error": str(ex)[:100]}
 
     if rank == 0:
         line = {
