@@ -1365,6 +1365,7 @@ bool Engine::prune(View& v, std::vector<WeightPost>& weights, std::vector<Cluste
   if ((int)keep.size() == K) return false;
   if (verbose_) std::cout << '*' << std::flush;
   list_valid_ = false;
+  score_valid_ = false;  // columns go away and the weights are updated: the ranking is recomputed
   std::vector<ClusterPost> nc;
   std::vector<std::vector<double>> nh;
   for (int32_t k : keep) {
@@ -1412,8 +1413,22 @@ bool Engine::split_gr(View& v, std::vector<WeightPost>& weights, std::vector<Clu
   // rank clusters by their approximate free-energy contribution (cluster.cpp:386-418)
   std::vector<double> H, Njk;
   v_ntot_ = N_total_;
-  ephase(v, weights, clusters, dev::kEScore, &H);
-  const double cbar = H.back();
+  double cbar;
+  // every rank must take the same branch (the fallback holds a collective): agree on the validity first
+  double have = (score_valid_ && score_q_ == v.q && score_K_ == K && !host_stale_) ? 1.0 : 0.0;
+  allreduce_host(&have, 1);
+  if (have == (double)world_) {
+    // the last E pass of the fit's vbem() already summed q * logit per cluster (estep_finalize_kernel)
+    H.resize(K);
+    check(cudaMemcpyAsync(H.data(), d_score_.p, sizeof(double) * (size_t)K, cudaMemcpyDeviceToHost, stream_), "D2H scores");
+    sync();
+    allreduce_host(H.data(), K);
+    cbar = score_cbar_;
+  } else {
+    ephase(v, weights, clusters, dev::kEScore, &H);
+    cbar = H.back();
+  }
+  score_valid_ = false;
   group_counts(v, Njk);
   std::vector<GreedOrder> ord(K);
   for (int k = 0; k < K; ++k) {
@@ -1589,6 +1604,12 @@ void Engine::learn(int model, double prior, double wprior, int maxclusters, bool
     ~ThreadsGuard() { ref = saved; }
   } tguard{host_threads_, host_threads_};
   host_threads_ = (int)std::max(1u, std::min((unsigned)host_threads_, nthreads));
+  struct ScoreGuard {
+    bool& want;
+    bool& valid;
+    ~ScoreGuard() { want = false; valid = false; }
+  } sguard{want_scores_, score_valid_};
+  want_scores_ = true;
   model_init(model, prior, wprior, sparse);
   verbose_ = verbose;
   list_valid_ = false;

@@ -129,6 +129,13 @@ class Engine {
   long long elist_cap_ = 0, slist_cap_ = 0;   // capacity (entries) of the candidate lists / the non-zero lists
   double last_pairs_ = 0, last_nnz_s_ = 0;
   double* h_iter_ = nullptr;    // page-locked copy of the iteration record
+  // split scores sum_n q_nk logit_nk left by the last two-level E pass of a fit (Engine::split_gr uses them instead of
+  // a ranking pass over the data while they still describe the current q and model)
+  bool want_scores_ = false, score_valid_ = false;
+  const void* score_q_ = nullptr;
+  int score_K_ = 0;
+  double score_cbar_ = 0;
+  DeviceBuf d_score_;
   DeviceBuf d_raw_, d_post_, d_work_, d_iter_, d_centre_, d_wscr_, d_vaug_;
   void allreduce_host(double* host, int64_t count);
   void share_host_threads();

@@ -380,7 +380,13 @@ void Engine::dev_two_level(View& v, int K, const TcLayout& lay, bool first_try) 
     check(cudaEventRecord(ev_[8], stream_), "event");
     return;
   }
-  check(dev::estep_finalize(stream_, sms_, q, v.ldq, v.N, K, cmask, it + dev::kItSumLogZ, skip), "estep_finalize");
+  double* d_H = nullptr;
+  if (want_scores_ && !sparse_) {
+    reserve(d_score_, sizeof(double) * (size_t)K);
+    d_H = (double*)d_score_.p;
+    check(cudaMemsetAsync(d_H, 0, sizeof(double) * (size_t)K, stream_), "memset scores");
+  }
+  check(dev::estep_finalize(stream_, sms_, q, v.ldq, v.N, K, cmask, it + dev::kItSumLogZ, skip, d_H), "estep_finalize");
   ++launches_;
   check(cudaEventRecord(ev_[8], stream_), "event");
 }
@@ -400,6 +406,7 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
   unsigned* d_err = (unsigned*)d_err_.p;
   double rec[24];
   bool try_two = false, two_done = false;
+  score_valid_ = false;
   TcLayout lay{};
   for (double& x : estep_detail_) x = 0;
   for (int attempt = 0;; ++attempt) {
@@ -568,6 +575,13 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
       if (cudaEventElapsedTime(&ms, ev_[6], ev_[7]) == cudaSuccess) estep_detail_[2] = ms;
       if (cudaEventElapsedTime(&ms, ev_[7], ev_[8]) == cudaSuccess) estep_detail_[3] = ms;
       cudaGetLastError();
+      if (want_scores_ && !sparse_ && tc_stage_ == 0) {
+        // the split ranking of this model on these responsibilities came with the soft-max pass
+        score_valid_ = true;
+        score_q_ = v.q;
+        score_K_ = K;
+        score_cbar_ = rec[dev::kItCbar];
+      }
       if (tc_stage_ == 0 && !sparse_ && rec[dev::kItPairs] > 0) {
         list_valid_ = true;
         list_q_ = v.q;

@@ -1643,9 +1643,17 @@ estep_coarse_tc128_kernel(const float* __restrict__ X, const float* __restrict__
 template <int LGP>  // log2 of the lanes that share a row in phase B: 4 << LGP >= K
 __global__ void __launch_bounds__(256)
 estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, const uint32_t* __restrict__ cmask, int W,
-                      double* __restrict__ Fz, const unsigned* __restrict__ skip) {
+                      double* __restrict__ Fz, const unsigned* __restrict__ skip, double* __restrict__ Hk) {
   constexpr int GP = 1 << LGP, WMAX = (4 * GP + 31) / 32;
   if (skip != nullptr && (skip[0] | skip[1]) != 0u) return;
+  // Optional split scores H_k = sum_n q_nk * logit_nk (the ranking of split_gr, src/cluster.cpp:401-415, from the
+  // quantities this pass holds anyway; only fits ask for them): per-CTA fp64 sums in shared memory, one global atomic
+  // per cluster and CTA.
+  __shared__ double sH[4 * GP];
+  if (Hk != nullptr) {
+    for (int k = threadIdx.x; k < 4 * GP; k += blockDim.x) sH[k] = 0.0;
+    __syncthreads();
+  }
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -1683,6 +1691,18 @@ estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, cons
       fz += (double)(logf(se) + mx);
     }
     const float inv = se > 0.f ? 1.0f / se : 0.f;
+    if (Hk != nullptr && se > 0.f) {
+#pragma unroll
+      for (int w = 0; w < WMAX; ++w) {
+        uint32_t word = mw[w];
+        while (word) {
+          const int k = 32 * w + __ffs(word) - 1;
+          word &= word - 1;
+          const float e = qrow[k];   // exp(logit - max), parked above
+          if (e > 0.f) atomicAdd(&sH[k], (double)(e * inv) * ((double)mx + (double)logf(e)));
+        }
+      }
+    }
     __syncwarp();  // the parked values are read by other lanes below
     // ---- phase B ----
 #pragma unroll 4
@@ -1721,6 +1741,11 @@ estep_finalize_kernel(float* __restrict__ q, int64_t ldq, int64_t N, int K, cons
   }
   for (int o = 16; o > 0; o >>= 1) fz += __shfl_xor_sync(0xffffffffu, fz, o);
   if (lane == 0 && fz != 0.0) atomicAdd(Fz, fz);
+  if (Hk != nullptr) {
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+      if (sH[k] != 0.0) atomicAdd(&Hk[k], sH[k]);
+  }
 }
 
 // q[n][k] = -inf where the candidate bit is clear (only the LCB_TC_STAGE test modes look at this)
@@ -1918,15 +1943,15 @@ cudaError_t estep_coarse_tc128(cudaStream_t st, int sms, const float* X, const f
 }
 
 cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
-                           double* Fz, const unsigned* skip) {
+                           double* Fz, const unsigned* skip, double* Hk) {
   if (N <= 0) return cudaSuccess;
   if (K > 256 || (ldq & 3)) return cudaErrorInvalidValue;
   const int W = (K + 31) / 32;
   const int grid = sms * 16;
-  if (K <= 32) estep_finalize_kernel<3><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
-  else if (K <= 64) estep_finalize_kernel<4><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
-  else if (K <= 128) estep_finalize_kernel<5><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
-  else estep_finalize_kernel<6><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip);
+  if (K <= 32) estep_finalize_kernel<3><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip, Hk);
+  else if (K <= 64) estep_finalize_kernel<4><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip, Hk);
+  else if (K <= 128) estep_finalize_kernel<5><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip, Hk);
+  else estep_finalize_kernel<6><<<grid, 256, 0, st>>>(q, ldq, N, K, cmask, W, Fz, skip, Hk);
   return cudaGetLastError();
 }
 

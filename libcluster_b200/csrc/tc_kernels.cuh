@@ -51,8 +51,9 @@ cudaError_t estep_tc128_list(cudaStream_t st, int sms, const float* X, int64_t N
                              const int32_t* itoff, int64_t nitems, void* items, float* q, int64_t ldq, unsigned* err,
                              const long long* nitems_dev = nullptr, const unsigned* skip = nullptr, int dim = 128);
 // level 3: q = softmax over the candidate logits (0 elsewhere), Fz += sum log Z
+//          Hk (optional, [K], accumulated): split scores sum_n q_nk * logit_nk
 cudaError_t estep_finalize(cudaStream_t st, int sms, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask,
-                           double* Fz, const unsigned* skip = nullptr);
+                           double* Fz, const unsigned* skip = nullptr, double* Hk = nullptr);
 // q = -inf outside the candidate mask (test modes only)
 cudaError_t apply_candidate_mask(cudaStream_t st, float* q, int64_t ldq, int64_t N, int K, const uint32_t* cmask);
 // lq[e] = q[lrow[e]][k] over the lists, Nk[k] += sum (grouped models, gid != NULL: Nk[gid[row]][k]): lets the
