@@ -936,7 +936,8 @@ double Engine::ephase(View& v, const std::vector<WeightPost>& weights, const std
                                          (const double*)dMh, (const double*)dMl, (const double*)dC, (const double*)dW,
                                          d_act, (double*)v.q, v.ldq, mode, d_fz, d_H);
   }
-  if (ke == cudaErrorInvalidValue) throw_invalid("unsupported (D, K) for the E-step kernel at this precision");
+  if (ke == cudaErrorInvalidValue) throw_invalid("the CUDA-core E-step kernels take at most 512 clusters and 256 dimensions (full covariance); beyond "
+                                                   "that only D = 128 or 64 in LCB_F32 (tensor-core tier) is supported");
   check(ke, "estep kernel");
   ++launches_;
   check(cudaEventRecord(ev_[3], stream_), "event");

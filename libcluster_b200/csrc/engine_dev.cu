@@ -519,7 +519,8 @@ void Engine::dev_iteration(View& v, const std::vector<WeightPost>& weights, doub
                                              (const double*)a.mhi, (const double*)a.mlo, (const double*)a.chat,
                                              (const double*)a.lw, d_act, (double*)v.q, v.ldq, dev::kEWrite, d_fz, d_H, skipE);
       }
-      if (ke == cudaErrorInvalidValue) throw_invalid("unsupported (D, K) for the E-step kernel at this precision");
+      if (ke == cudaErrorInvalidValue) throw_invalid("the CUDA-core E-step kernels take at most 512 clusters and 256 dimensions (full covariance); beyond "
+                                                   "that only D = 128 or 64 in LCB_F32 (tensor-core tier) is supported");
       check(ke, "estep kernel");
       ++launches_;
     }
