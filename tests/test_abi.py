@@ -168,3 +168,23 @@ def test_device_stick_order_is_std_sort(n):
         assert diff == 0
         assert sorted(order.tolist()) == list(range(n))
         assert np.all(np.diff(v[order]) <= 0)
+
+
+def test_dropin_headers_compile_and_link(tmp_path):
+    """CPU: the reference-facing C++ headers (include/libcluster.h, include/distributions.h) compile as a user program
+    (tests/cpp/dropin_main.cpp, written against the reference's API) against the Eigen stand-in and link to the C-ABI
+    library.  Running it needs a GPU (tests/test_gpu_cpp_dropin.py); this only guards the boundary's syntax and
+    symbols, including the weight-prior accessor the fits read (src/cluster.cpp:653,684)."""
+    import shutil
+    import subprocess
+    cxx = shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    libdir = os.path.join(ROOT, "libcluster_b200", "_lib")
+    exe = tmp_path / "dropin"
+    subprocess.check_call([cxx, "-std=c++11", "-O0", "-w", "-I" + os.path.join(ROOT, "oracle", "refshim"),
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "dropin_main.cpp"),
+                           "-o", str(exe), "-L" + libdir, "-llcb200", "-Wl,-rpath," + libdir])
+    assert exe.exists()
+    hdr = open(os.path.join(ROOT, "include", "libcluster.h")).read()
+    assert "common_weight_prior" in hdr and "lcb_learn(g.e, model, clusterprior, wprior" in hdr
