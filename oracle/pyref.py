@@ -29,6 +29,7 @@ def lib():
         dp, lp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p
         L.ref_last_error.restype = C.c_char_p
         L.ref_learn.argtypes = [C.c_int, C.c_int, dp, lp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]
+        L.ref_learn_wprior.argtypes = [C.c_int, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint, C.POINTER(vp)]
         L.ref_vbem.argtypes = [C.c_int, C.c_int, dp, lp, C.c_int, dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
         L.ref_free.argtypes = [vp]
         L.ref_F.restype = C.c_double
@@ -94,9 +95,19 @@ def _pack(groups):
     return cat, Nj, groups[0].shape[1], len(groups)
 
 
-def learn(model, groups, prior=1.0, maxclusters=-1, sparse=False, nthreads=1):
+def learn(model, groups, prior=1.0, maxclusters=-1, sparse=False, nthreads=1, weight_prior=None):
+    """learnXXX of the reference.  weight_prior (single-group models): the caller passes Dirichlet(alpha) /
+    StickBreak(concentration) instead of a default-constructed weight object."""
     cat, Nj, D, J = _pack(groups)
     h = C.c_void_p()
+    if weight_prior is not None:
+        assert J == 1
+        rc = lib().ref_learn_wprior(model, _dp(cat), int(Nj[0]), D, prior, weight_prior, maxclusters, nthreads, C.byref(h))
+        if rc:
+            msg = lib().ref_last_error().decode()
+            lib().ref_free(h)
+            raise RefError(rc, msg)
+        return Result(h, D)
     rc = lib().ref_learn(model, J, _dp(cat), Nj.ctypes.data_as(C.POINTER(C.c_int64)), D, prior, maxclusters, int(sparse),
                          nthreads, C.byref(h))
     if rc:

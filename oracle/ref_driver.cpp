@@ -127,6 +127,39 @@ int ref_learn(int model, int J, const double* Xcat, const int64_t* Nj, int D, do
   return 0;
 }
 
+// The single-group entry points with a caller-constructed weight object (Dirichlet(alpha) / StickBreak(concentration)):
+// the fit keeps that prior (src/cluster.cpp:653,684) while split refinements use default-constructed weights (:460-461)
+int ref_learn_wprior(int model, const double* Xcat, int64_t N, int D, double prior, double wprior, int maxclusters,
+                     unsigned nthreads, void** out) {
+  RefResult* r = new RefResult();
+  *out = r;
+  try {
+    const int64_t Nj[1] = {N};
+    vMatrixXd X = to_groups(1, Xcat, Nj, D);
+    MatrixXd q;
+    if (model == 0) {
+      StickBreak w(wprior); std::vector<GaussWish> c;
+      r->F = learnVDP(X[0], q, w, c, prior, maxclusters, false, nthreads);
+      harvest(r, vMatrixXd(1, q), std::vector<StickBreak>(1, w), c, D);
+    } else if (model == 1) {
+      Dirichlet w(wprior); std::vector<GaussWish> c;
+      r->F = learnBGMM(X[0], q, w, c, prior, maxclusters, false, nthreads);
+      harvest(r, vMatrixXd(1, q), std::vector<Dirichlet>(1, w), c, D);
+    } else if (model == 2) {
+      Dirichlet w(wprior); std::vector<NormGamma> c;
+      r->F = learnDGMM(X[0], q, w, c, prior, maxclusters, false, nthreads);
+      harvest(r, vMatrixXd(1, q), std::vector<Dirichlet>(1, w), c, D);
+    } else {
+      g_err = "ref_learn_wprior: single-group models only";
+      return 1;
+    }
+  } catch (const std::invalid_argument& e) { g_err = e.what(); return 1;
+  } catch (const std::runtime_error& e) { g_err = e.what(); return 2;
+  } catch (const std::exception& e) { g_err = e.what(); return 3;
+  } catch (...) { g_err = "unknown"; return 3; }
+  return 0;
+}
+
 // vbem<W,C>() (src/cluster.cpp:177) from caller-supplied responsibilities q0 [N x K] row-major
 int ref_vbem(int model, int J, const double* Xcat, const int64_t* Nj, int D, const double* q0, int K, double prior,
              int maxit, int sparse, int nthreads, void** out) {

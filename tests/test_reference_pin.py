@@ -39,7 +39,9 @@ def test_reference_learn_on_its_own_fixture_equals_oracle_and_golden(testdata, n
 
 
 @pytest.mark.parametrize("model,D,K,diag", [(po.BGMM, 5, 4, False), (po.VDP, 12, 3, False), (po.DGMM, 9, 5, True),
-                                            (po.GMC, 3, 3, False), (po.DGMC, 4, 3, True)])
+                                            (po.GMC, 3, 3, False), (po.DGMC, 4, 3, True),
+                                            # the dimensions of the tensor-core tier (configs 2-4 of BASELINE.json)
+                                            (po.BGMM, 64, 4, False), (po.GMC, 64, 3, False), (po.VDP, 128, 3, False)])
 def test_reference_vbem_iterations_equal_oracle(model, D, K, diag):
     """vbem<W,C>() of src/cluster.cpp:177 called directly, for every iteration count up to 4."""
     X, z = make_blobs(600, D, K, seed=D * 7, spread=4.0, diag=diag)
@@ -64,6 +66,28 @@ def test_reference_learn_with_splits_and_sparse_equals_oracle():
         assert r.K == m.K
         assert r.F == pytest.approx(F, rel=1e-11)
         assert np.abs(np.concatenate(r.qZ, 0) - m.qZ()).max() < 1e-10
+
+
+@pytest.mark.parametrize("model,wp", [(po.BGMM, 5.0), (po.VDP, 3.0), (po.DGMM, 0.2), (po.VDP, 0.5)])
+def test_reference_keeps_a_callers_weight_prior_like_the_oracle(testdata, model, wp):
+    """learnBGMM(X, qZ, Dirichlet(alpha), ...) / learnVDP(X, qZ, StickBreak(c), ...): the fit keeps the caller's prior
+    (src/cluster.cpp:653,684) while the split refinements use default-constructed weights (:460-461).  This is what the
+    C++ drop-in header forwards to lcb_learn (tests/test_gpu_cpp_dropin.py compares the engine with the oracle)."""
+    X, _ = testdata
+    Xcat = np.concatenate(list(X), 0)
+    r = pyref.learn(model, [Xcat], weight_prior=wp)
+    m = po.Model(model, [Xcat])
+    F = m.learn(weight_prior=wp)
+    assert r.K == m.K
+    assert r.F == pytest.approx(F, rel=1e-12)
+    assert np.abs(r.qZ[0] - m.qZ()).max() < 1e-11
+    assert np.allclose(r.Elogweight[0], m.weights(0)[0], rtol=1e-12, atol=1e-13)
+    assert r.wfen[0] == pytest.approx(m.weights_fenergy(0), rel=1e-11, abs=1e-11)
+    # and it is not the default-prior fit
+    assert abs(F - po.Model(model, [Xcat]).learn()) > 1e-6 * abs(F)
+    with pytest.raises(pyref.RefError) as e:
+        pyref.learn(model, [Xcat], weight_prior=0.0)     # distributions.cpp:107,234
+    assert e.value.code == 1
 
 
 def test_reference_error_behaviour():
