@@ -29,7 +29,8 @@ def lib():
         dp, lp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_void_p
         L.ref_last_error.restype = C.c_char_p
         L.ref_learn.argtypes = [C.c_int, C.c_int, dp, lp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_uint, C.POINTER(vp)]
-        L.ref_learn_wprior.argtypes = [C.c_int, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint, C.POINTER(vp)]
+        if hasattr(L, "ref_learn_wprior"):   # absent from a library built before round 2
+            L.ref_learn_wprior.argtypes = [C.c_int, dp, C.c_int64, C.c_int, C.c_double, C.c_double, C.c_int, C.c_uint, C.POINTER(vp)]
         L.ref_vbem.argtypes = [C.c_int, C.c_int, dp, lp, C.c_int, dp, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
         L.ref_free.argtypes = [vp]
         L.ref_F.restype = C.c_double
